@@ -1,0 +1,233 @@
+// elementwise.cuh — the HBM-bound helpers of the forward: fused stem conv (1x7 s2 + BN + ReLU +
+// maxpool 1x3 s2), the two pooling shapes, LSTM layer-0 feature rows and the fused head.
+// All kernels work on the padded row layout: sample s, position p -> row s*Lp + p, rows with
+// p >= L are zero ("halo" rows shared between neighbouring samples).
+#pragma once
+#include "ops.cuh"
+
+namespace dsb {
+
+// ---- 8-channel vector helpers (16 B for bf16, 32 B for fp32) -------------------------------------
+template <class T> struct Vec8;
+template <> struct Vec8<float> {
+  float v[8];
+  __device__ __forceinline__ static Vec8 load(const float* p) {
+    Vec8 r;
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  float v[8];
+  __device__ __forceinline__ static Vec8 load(const __nv_bfloat16* p) {
+    Vec8 r;
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    return r;
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// ---- stem: signals [n][S] fp32 -> P1 [n*Lp2][64] --------------------------------------------------
+// conv 1x7 stride 2 SAME (1->64) + folded BN + ReLU at L1 positions, then maxpool 1x3 stride 2 SAME
+// (reference layers.py:183-191).  One CTA per sample, 256 threads; thread -> (channel, position stripe).
+struct StemParams {
+  const float* signals; int S;
+  const float* w;      // [64][7] folded
+  const float* bias;   // [64]
+  int L1, L2, Lp2, conv_pl, pool_pl;
+  void* out;           // [n*Lp2][64]
+  int n;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
+  extern __shared__ float sm[];
+  float* xs = sm;                       // S + 16 (zero padded both sides by 8)
+  float* ws = xs + p.S + 16;            // 64*7
+  float* bs = ws + 64 * 7;              // 64
+  const int s = blockIdx.x;
+  for (int i = threadIdx.x; i < p.S + 16; i += blockDim.x) {
+    const int j = i - 8;
+    xs[i] = (j >= 0 && j < p.S) ? p.signals[(size_t)s * p.S + j] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 64 * 7; i += blockDim.x) ws[i] = p.w[i];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) bs[i] = p.bias[i];
+  __syncthreads();
+  T* out = reinterpret_cast<T*>(p.out) + (size_t)s * p.Lp2 * 64;
+  const int c = threadIdx.x & 63;
+  float w[7];
+#pragma unroll
+  for (int t = 0; t < 7; ++t) w[t] = ws[c * 7 + t];
+  const float b = bs[c];
+  for (int pos = threadIdx.x >> 6; pos < p.Lp2; pos += blockDim.x >> 6) {
+    float best = 0.f;   // ReLU output >= 0 and every pool window holds >= 1 valid cell
+    if (pos < p.L2) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int q = 2 * pos - p.pool_pl + k;      // conv1 position
+        if (q < 0 || q >= p.L1) continue;
+        const int x0 = 2 * q - p.conv_pl + 8;       // index into xs
+        float a = b;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) a = fmaf(w[t], xs[x0 + t], a);
+        best = fmaxf(best, a);
+      }
+    }
+    out[(size_t)pos * 64 + c] = from_f32<T>(best);
+  }
+}
+
+// ---- maxpool 1x3 stride 1 SAME over rows (inputs >= 0, halo rows are zero) -------------------------
+template <class T>
+__global__ void pool3s1_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t M, int C) {
+  const int cv = C / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * cv) return;
+  const int64_t r = idx / cv;
+  const int c = (int)(idx % cv) * 8;
+  Vec8<T> a = Vec8<T>::load(x + r * C + c);
+  if (r > 0) {
+    const Vec8<T> b = Vec8<T>::load(x + (r - 1) * C + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a.v[i] = fmaxf(a.v[i], b.v[i]);
+  }
+  if (r + 1 < M) {
+    const Vec8<T> b = Vec8<T>::load(x + (r + 1) * C + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a.v[i] = fmaxf(a.v[i], b.v[i]);
+  }
+  a.store(y + r * C + c);
+}
+
+// ---- maxpool 1x3 stride 2 SAME between stages (reference layers.py:211-213,224-226) ----------------
+template <class T>
+__global__ void pool3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, int C,
+                               int Lin, int Lpin, int Lout, int Lpout, int pl) {
+  const int cv = C / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * Lpout * cv) return;
+  const int c = (int)(idx % cv) * 8;
+  const int64_t ro = idx / cv;
+  const int64_t s = ro / Lpout;
+  const int po = (int)(ro % Lpout);
+  Vec8<T> a;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a.v[i] = 0.f;
+  if (po < Lout) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int q = 2 * po - pl + k;
+      if (q < 0 || q >= Lin) continue;
+      const Vec8<T> b = Vec8<T>::load(x + (s * Lpin + q) * C + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a.v[i] = fmaxf(a.v[i], b.v[i]);
+    }
+  }
+  a.store(y + ro * C + c);
+}
+
+// ---- LSTM layer-0 feature rows: F[pos][n][FW] = onehot(code) | mean | std | len | 0... -------------
+template <class T>
+__global__ void lstm_feat_kernel(const int32_t* __restrict__ kmer, const float* __restrict__ means,
+                                 const float* __restrict__ stds, const float* __restrict__ lens,
+                                 T* __restrict__ F, int64_t n, int64_t cap, int klen, int FW, int use_base) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * klen) return;
+  const int64_t s = idx / klen;
+  const int pos = (int)(idx % klen);
+  T* f = F + ((int64_t)pos * cap + s) * FW;
+  const int code = use_base ? kmer[idx] : -1;
+  for (int j = 0; j < FW; ++j) {
+    float v = 0.f;
+    if (j < 5) v = (j == code) ? 1.f : 0.f;
+    else if (j == 5) v = means[idx];
+    else if (j == 6) v = stds[idx];
+    else if (j == 7) v = lens[idx];
+    f[j] = from_f32<T>(v);
+  }
+}
+
+// ---- head: logits = h_fw·Wr[0:256] + h_bw·Wr[256:512] + sum_{p,c} y[s*Lp+p][c]·Wc[p][c] ------------
+// (dense·dense_1 collapsed, avgpool folded into Wc; sigmoid + argmax fused; reference layers.py:250-264,
+// model.py:100,108).  One warp per sample.
+struct HeadParams {
+  const void* y; int Lp, L;           // final inception output [n*Lp][240] or nullptr
+  const void* hfw; const void* hbw;   // [n][256] or nullptr
+  const float* Wc;                    // [L*240][2]
+  const float* Wr;                    // [512][2]
+  float* probs; int32_t* pred; int64_t n;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= p.n) return;
+  float a0 = 0.f, a1 = 0.f;
+  if (p.y != nullptr) {
+    const T* y = reinterpret_cast<const T*>(p.y) + s * p.Lp * CH;
+    const int nv = p.L * CH / 8;                 // contiguous: rows 0..L-1 of this sample
+    for (int i = lane; i < nv; i += 32) {
+      const Vec8<T> v = Vec8<T>::load(y + i * 8);
+      const float4* w = reinterpret_cast<const float4*>(p.Wc + (size_t)i * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 ww = __ldg(w + q);
+        a0 = fmaf(v.v[2 * q], ww.x, a0); a1 = fmaf(v.v[2 * q], ww.y, a1);
+        a0 = fmaf(v.v[2 * q + 1], ww.z, a0); a1 = fmaf(v.v[2 * q + 1], ww.w, a1);
+      }
+    }
+  }
+  if (p.hfw != nullptr) {
+    const T* hf = reinterpret_cast<const T*>(p.hfw) + s * HID;
+    const T* hb = reinterpret_cast<const T*>(p.hbw) + s * HID;
+    {
+      const Vec8<T> v = Vec8<T>::load(hf + lane * 8);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 ww = __ldg(reinterpret_cast<const float2*>(p.Wr) + lane * 8 + q);
+        a0 = fmaf(v.v[q], ww.x, a0); a1 = fmaf(v.v[q], ww.y, a1);
+      }
+    }
+    {
+      const Vec8<T> v = Vec8<T>::load(hb + lane * 8);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 ww = __ldg(reinterpret_cast<const float2*>(p.Wr) + HID + lane * 8 + q);
+        a0 = fmaf(v.v[q], ww.x, a0); a1 = fmaf(v.v[q], ww.y, a1);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if (lane == 0) {
+    const float p0 = 1.0f / (1.0f + expf(-a0)), p1 = 1.0f / (1.0f + expf(-a1));
+    p.probs[2 * s] = p0;
+    p.probs[2 * s + 1] = p1;
+    p.pred[s] = (p1 > p0) ? 1 : 0;     // argmax, ties -> 0
+  }
+}
+
+}  // namespace dsb

@@ -1,0 +1,571 @@
+// forward.cu — the call_mods forward (reference model.py:57-108 + layers.py) as a static plan of
+// GEMM-with-epilogue ops and a few HBM-bound helpers, executed chunk by chunk on device-resident
+// inputs.  Two backends share the plan: fp32 CUDA-core GEMMs (DSB_PREC_FP32) and bf16 tcgen05
+// GEMMs (DSB_PREC_BF16).
+//
+// Activation layout ("padded rows"): a stage with L positions stores sample s, position p at row
+// s*(L+HALO)+p of a row-major [rows][C] matrix; the HALO rows after each sample are zero, so a k-tap
+// conv is a sum of row-shifted GEMMs and a sample never sees its neighbour.
+#include <algorithm>
+#include <array>
+#include <cstdlib>
+#include <type_traits>
+
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+
+namespace dsb {
+
+enum StepKind { ST_GEMM, ST_STEM, ST_POOL1, ST_POOL2, ST_FEAT, ST_HEAD, ST_ZERO };
+
+struct SegHost { const void* a; int ld; int cols; int col0; int drow; int K; int map_rows_per_sample; };
+
+struct Step {
+  int kind = ST_GEMM;
+  int stream = 0;             // 0 cnn, 1 fw lstm, 2 bw lstm
+  int rows_per_sample = 1;    // M = n * rows_per_sample
+  // GEMM
+  GemmF32Params f32;
+  TcLaunch tc;
+  int epi_kind = EPI_CONV;
+  int kclass = KC_GEMM;
+  double flops_per_row = 0;
+  // helpers
+  StemParams stem;
+  const void* src = nullptr; void* dst = nullptr;
+  int C = 0, Lin = 0, Lpin = 0, Lout = 0, Lpout = 0, pl = 0;
+  size_t zero_bytes_per_sample = 0;
+  HeadParams head;
+};
+
+struct ForwardPlan {
+  int precision = 0;
+  int64_t cap = 0;            // samples per chunk the buffers are sized for
+  DevBuf weights, work;
+  std::vector<Step> steps;
+  void* F = nullptr; int FW = 0;
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  bool multi_stream = true;
+  size_t work_bytes = 0;
+  ~ForwardPlan() {
+    for (auto s : side) if (s) cudaStreamDestroy(s);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (auto e : ev_join) if (e) cudaEventDestroy(e);
+  }
+};
+
+void destroy_plan(ForwardPlan* p) { delete p; }
+
+namespace {
+
+struct Arena {          // bump allocator over one DevBuf (two passes: size, then place)
+  uint8_t* base = nullptr;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~(size_t)1023;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+template <class T> struct DevGemm { const T* w; const float* bias; int N; int Ktot; };
+
+// Upload a folded GEMM: K is re-laid out as the concatenation of `parts` (src_k0, len, padded_len).
+template <class T>
+DevGemm<T> upload_gemm(Arena& wa, const FoldedGemm& g, const std::vector<std::array<int, 3>>& parts, cudaStream_t s) {
+  int Ktot = 0;
+  for (auto& p : parts) Ktot += p[2];
+  DevGemm<T> d{nullptr, nullptr, g.N, Ktot};
+  T* w = reinterpret_cast<T*>(wa.take((size_t)g.N * Ktot * sizeof(T)));
+  float* b = reinterpret_cast<float*>(wa.take((size_t)g.N * sizeof(float)));
+  d.w = w;
+  d.bias = b;
+  if (wa.base) {
+    std::vector<T> h((size_t)g.N * Ktot);
+    for (int n = 0; n < g.N; ++n) {
+      int ko = 0;
+      for (auto& p : parts) {
+        for (int k = 0; k < p[2]; ++k) {
+          const float v = (k < p[1]) ? g.w[(size_t)n * g.K + p[0] + k] : 0.f;
+          if constexpr (std::is_same<T, float>::value) h[(size_t)n * Ktot + ko + k] = v;
+          else h[(size_t)n * Ktot + ko + k] = __float2bfloat16_rn(v);
+        }
+        ko += p[2];
+      }
+    }
+    DSB_CUDA(cudaMemcpyAsync(w, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    DSB_CUDA(cudaMemcpyAsync(b, g.bias.data(), g.N * sizeof(float), cudaMemcpyHostToDevice, s));
+    DSB_CUDA(cudaStreamSynchronize(s));   // h goes out of scope
+  }
+  return d;
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+template <class T>
+struct Builder {
+  static constexpr bool TC = !std::is_same<T, float>::value;
+  dsb_ctx* ctx;
+  ForwardPlan& plan;
+  const FoldedModel& fm;
+  int64_t cap;
+  Arena wa, ba;       // weights, work buffers
+  bool place;         // second pass: pointers are real
+  cudaStream_t up_stream;
+
+  T* buf(size_t elems) { return reinterpret_cast<T*>(ba.take(elems * sizeof(T))); }
+
+  // one GEMM step -------------------------------------------------------------------------------
+  // alg_rows: rows per sample that carry real outputs (L for convs, 1 for the LSTM); kalg: algorithmic K
+  void gemm(int stream, int rows_per_sample, int64_t rows_cap, const std::vector<SegHost>& segs,
+            const DevGemm<T>& W, int BK, EpiParams epi, int epi_kind, int kclass, int alg_rows, int kalg) {
+    Step st;
+    st.kind = ST_GEMM;
+    st.stream = stream;
+    st.rows_per_sample = rows_per_sample;
+    st.epi_kind = epi_kind;
+    st.kclass = kclass;
+    epi.N = W.N;
+    epi.bias = W.bias;
+    st.flops_per_row = 2.0 * (double)kalg * W.N * (double)alg_rows / (double)rows_per_sample;
+    if (!place) { plan.steps.push_back(st); return; }
+    if constexpr (!TC) {
+      GemmF32Params& g = st.f32;
+      g.nseg = (int)segs.size();
+      int kt = 0;
+      for (int i = 0; i < g.nseg; ++i) {
+        g.seg[i] = SegF32{reinterpret_cast<const float*>(segs[i].a), segs[i].ld, segs[i].col0, segs[i].drow, round_up(segs[i].K, 16)};
+        kt += g.seg[i].K;
+      }
+      if (kt != W.Ktot) fail(DSB_ERR_STATE, "internal: fp32 GEMM K mismatch %d vs %d", kt, W.Ktot);
+      g.B = reinterpret_cast<const float*>(W.w);
+      g.Ktot = W.Ktot;
+      g.epi = epi;
+    } else {
+      TcLaunch& L = st.tc;
+      L.BK = BK;
+      L.epi_kind = epi_kind;
+      L.p.nseg = (int)segs.size();
+      const void* map_base[2] = {nullptr, nullptr};
+      int nmaps = 0, kt = 0;
+      for (int i = 0; i < L.p.nseg; ++i) {
+        int mi = -1;
+        for (int j = 0; j < nmaps; ++j) if (map_base[j] == segs[i].a) mi = j;
+        if (mi < 0) {
+          if (nmaps == 2) fail(DSB_ERR_STATE, "internal: more than two A matrices in one GEMM");
+          mi = nmaps++;
+          map_base[mi] = segs[i].a;
+          encode_map_bf16(&L.maps.a[mi], segs[i].a, rows_cap, segs[i].cols, segs[i].ld, 128, BK);
+        }
+        const int nkb = round_up(segs[i].K, BK) / BK;
+        L.p.seg[i] = SegTC{mi, segs[i].col0, segs[i].drow, nkb};
+        kt += nkb * BK;
+      }
+      if (nmaps == 1) L.maps.a[1] = L.maps.a[0];
+      if (kt != W.Ktot) fail(DSB_ERR_STATE, "internal: bf16 GEMM K mismatch %d vs %d", kt, W.Ktot);
+      L.p.BN = W.N <= 256 ? W.N : 256;
+      encode_map_bf16(&L.maps.b, W.w, W.N, W.Ktot, W.Ktot, L.p.BN, BK);
+      L.p.epi = epi;
+      L.flops_per_row = st.flops_per_row;
+      finalize_tc_launch(L);
+    }
+    plan.steps.push_back(st);
+  }
+
+  std::vector<std::array<int, 3>> kparts(std::initializer_list<std::pair<int, int>> src, int BK) {
+    std::vector<std::array<int, 3>> v;
+    const int pad = TC ? BK : 16;
+    for (auto& p : src) v.push_back({p.first, p.second, round_up(p.second, pad)});
+    return v;
+  }
+  std::vector<std::array<int, 3>> tap_parts(int taps, int cin, int BK) {
+    std::vector<std::array<int, 3>> v;
+    const int pad = TC ? BK : 16;
+    for (int t = 0; t < taps; ++t) v.push_back({t * cin, cin, round_up(cin, pad)});
+    return v;
+  }
+
+  void build() {
+    const int S = fm.signal_len, KL = fm.kmer_len;
+    const int L2 = fm.L2, L3 = fm.L3, L4 = fm.L4;
+    const int Lp2 = L2 + HALO, Lp3 = L3 + HALO, Lp4 = L4 + HALO;
+    const int64_t R2 = cap * Lp2;
+    void* final_y = nullptr;
+    int final_Lp = Lp4;
+
+    if (fm.has_cnn()) {
+      // ---- device weights ----
+      float* w1 = reinterpret_cast<float*>(wa.take(64 * 7 * sizeof(float)));
+      float* b1 = reinterpret_cast<float*>(wa.take(64 * sizeof(float)));
+      if (place) {
+        DSB_CUDA(cudaMemcpyAsync(w1, fm.conv1.w.data(), 64 * 7 * sizeof(float), cudaMemcpyHostToDevice, up_stream));
+        DSB_CUDA(cudaMemcpyAsync(b1, fm.conv1.bias.data(), 64 * sizeof(float), cudaMemcpyHostToDevice, up_stream));
+      }
+      DevGemm<T> Wc2 = upload_gemm<T>(wa, fm.conv2, kparts({{0, 64}}, 64), up_stream);
+      DevGemm<T> Wc3 = upload_gemm<T>(wa, fm.conv3, tap_parts(3, 128, 64), up_stream);
+      // ---- buffers ----
+      T* P1 = buf((size_t)R2 * 64);
+      T* C2 = buf((size_t)R2 * 128);
+      T* X0 = buf((size_t)R2 * 256);
+      T* XP = buf((size_t)R2 * 256);
+      T* YA = buf((size_t)R2 * CH);
+      T* YB = buf((size_t)R2 * CH);
+      T* Tb = buf((size_t)R2 * 144);
+      T* Ub = buf((size_t)R2 * 64);
+
+      // stem
+      {
+        Step st;
+        st.kind = ST_STEM;
+        st.stream = 0;
+        const int conv_total = std::max((fm.L1 - 1) * 2 + 7 - S, 0);
+        const int pool_total = std::max((L2 - 1) * 2 + 3 - fm.L1, 0);
+        st.stem = StemParams{nullptr, S, w1, b1, fm.L1, L2, Lp2, conv_total / 2, pool_total / 2, P1, 0};
+        plan.steps.push_back(st);
+      }
+      auto conv_epi = [&](void* d0, int ld0, int c0, uint32_t relu, int Lp, int L) {
+        EpiParams e;
+        e.d0 = d0; e.ld0 = ld0; e.c0 = c0; e.split = 1 << 30; e.relu_mask = relu; e.Lp = Lp; e.L = L;
+        return e;
+      };
+      gemm(0, Lp2, R2, {SegHost{P1, 64, 64, 0, 0, 64, Lp2}}, Wc2, 64, conv_epi(C2, 128, 0, 0xffffffffu, Lp2, L2), EPI_CONV, KC_GEMM, L2, 64);
+      gemm(0, Lp2, R2, {SegHost{C2, 128, 128, 0, -1, 128, Lp2}, SegHost{C2, 128, 128, 0, 0, 128, Lp2}, SegHost{C2, 128, 128, 0, 1, 128, Lp2}},
+           Wc3, 64, conv_epi(X0, 256, 0, 0xffffffffu, Lp2, L2), EPI_CONV, KC_GEMM, L2, 384);
+
+      const T* X = X0;
+      int xld = 256;
+      int L = L2, Lp = Lp2;
+      T* Y = YA;
+      for (int i = 0; i < NBLOCK; ++i) {
+        const FoldedBlock& fb = fm.blocks[i];
+        const int cin = fb.cin;
+        const int64_t rows_cap = cap * Lp;
+        DevGemm<T> Wb1 = upload_gemm<T>(wa, fb.b1, kparts({{0, cin}}, 64), up_stream);
+        DevGemm<T> Wp1 = upload_gemm<T>(wa, fb.p1, kparts({{0, cin}}, 64), up_stream);
+        DevGemm<T> Wb3 = upload_gemm<T>(wa, fb.b3, tap_parts(3, 32, 32), up_stream);
+        DevGemm<T> Wb4 = upload_gemm<T>(wa, fb.b4, tap_parts(5, 32, 32), up_stream);
+        DevGemm<T> Wb5b = upload_gemm<T>(wa, fb.b5b, tap_parts(3, 32, 32), up_stream);
+        DevGemm<T> Wb5c = upload_gemm<T>(wa, fb.b5c, kparts({{0, 64}}, 64), up_stream);
+        {   // branch-1 max pool (1x3, stride 1)
+          Step st;
+          st.kind = ST_POOL1;
+          st.stream = 0;
+          st.rows_per_sample = Lp;
+          st.src = X; st.dst = XP; st.C = xld;
+          plan.steps.push_back(st);
+        }
+        gemm(0, Lp, rows_cap, {SegHost{XP, xld, cin, 0, 0, cin, Lp}}, Wb1, 64, conv_epi(Y, CH, 0, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, cin);
+        {   // fused 1x1s: b2 -> Y[:,48:96] ; b3a|b4a|b5a|stem -> T[:,0:144] (stem without ReLU)
+          EpiParams e = conv_epi(Y, CH, 48, 0x1ffu /* cols 0..143 */, Lp, L);
+          e.split = 48;
+          e.d1 = Tb; e.ld1 = 144; e.c1 = 0;
+          gemm(0, Lp, rows_cap, {SegHost{X, xld, cin, 0, 0, cin, Lp}}, Wp1, 64, e, EPI_CONV, KC_GEMM, L, cin);
+        }
+        gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 0, -1, 32, Lp}, SegHost{Tb, 144, 144, 0, 0, 32, Lp}, SegHost{Tb, 144, 144, 0, 1, 32, Lp}},
+             Wb3, 32, conv_epi(Y, CH, 96, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 96);
+        gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 32, -2, 32, Lp}, SegHost{Tb, 144, 144, 32, -1, 32, Lp}, SegHost{Tb, 144, 144, 32, 0, 32, Lp},
+                               SegHost{Tb, 144, 144, 32, 1, 32, Lp}, SegHost{Tb, 144, 144, 32, 2, 32, Lp}},
+             Wb4, 32, conv_epi(Y, CH, 144, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 160);
+        gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 64, -1, 32, Lp}, SegHost{Tb, 144, 144, 64, 0, 32, Lp}, SegHost{Tb, 144, 144, 64, 1, 32, Lp}},
+             Wb5b, 32, conv_epi(Ub, 64, 0, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 96);
+        {
+          EpiParams e = conv_epi(Y, CH, 192, 0xffffffffu, Lp, L);
+          e.res = Tb; e.res_ld = 144; e.res_c0 = 96;
+          gemm(0, Lp, rows_cap, {SegHost{Ub, 64, 64, 0, 0, 64, Lp}}, Wb5c, 64, e, EPI_CONV, KC_GEMM, L, 64);
+        }
+        X = Y;
+        xld = CH;
+        T* other = (Y == YA) ? YB : YA;
+        if (i == 2 || i == 7) {   // max pool 1x3 stride 2 between stages
+          const int Lo = (i == 2) ? L3 : L4, Lpo = Lo + HALO;
+          const int total = std::max((Lo - 1) * 2 + 3 - L, 0);
+          Step st;
+          st.kind = ST_POOL2;
+          st.stream = 0;
+          st.src = Y; st.dst = other; st.C = CH; st.Lin = L; st.Lpin = Lp; st.Lout = Lo; st.Lpout = Lpo; st.pl = total / 2;
+          plan.steps.push_back(st);
+          X = other;
+          other = Y;
+          L = Lo; Lp = Lpo;
+        }
+        Y = other;
+      }
+      final_y = const_cast<T*>(X);
+      final_Lp = Lp;
+    }
+
+    void* hfw = nullptr;
+    void* hbw = nullptr;
+    if (fm.has_rnn()) {
+      const int FW = TC ? 64 : 16;
+      plan.FW = FW;
+      T* F = buf((size_t)KL * cap * FW);
+      plan.F = F;
+      {
+        Step st;
+        st.kind = ST_FEAT;
+        st.stream = 0;    // runs before the fork
+        plan.steps.insert(plan.steps.begin(), st);
+      }
+      for (int d = 0; d < 2; ++d) {
+        T* H[NLAYER];
+        float* Cst[NLAYER];
+        for (int l = 0; l < NLAYER; ++l) {
+          H[l] = buf((size_t)(KL + 1) * cap * HID);
+          Cst[l] = reinterpret_cast<float*>(ba.take((size_t)cap * HID * sizeof(float)));
+          Step z;
+          z.kind = ST_ZERO;
+          z.stream = 1 + d;
+          z.dst = H[l]; z.zero_bytes_per_sample = HID * sizeof(T);      // slot 0 = h_init
+          plan.steps.push_back(z);
+          Step zc = z;
+          zc.dst = Cst[l]; zc.zero_bytes_per_sample = HID * sizeof(float);
+          plan.steps.push_back(zc);
+        }
+        for (int l = 0; l < NLAYER; ++l) {
+          DevGemm<T> Wl = (l == 0)
+              ? upload_gemm<T>(wa, fm.lstm[d][l].g, std::vector<std::array<int, 3>>{{0, HID, HID}, {HID, 8, FW}}, up_stream)
+              : upload_gemm<T>(wa, fm.lstm[d][l].g, std::vector<std::array<int, 3>>{{0, HID, HID}, {HID, HID, HID}}, up_stream);
+          for (int t = 0; t < KL; ++t) {
+            const int pos = (d == 0) ? t : KL - 1 - t;          // bw consumes the k-mer reversed
+            T* hprev = H[l] + (size_t)t * cap * HID;
+            T* hnext = H[l] + (size_t)(t + 1) * cap * HID;
+            EpiParams e;
+            e.c = Cst[l];
+            e.h_out = hnext;
+            std::vector<SegHost> segs;
+            if (l == 0) {
+              segs.push_back(SegHost{hprev, HID, HID, 0, 0, HID, 1});
+              segs.push_back(SegHost{F + (size_t)pos * cap * FW, FW, FW, 0, 0, FW, 1});
+            } else {
+              segs.push_back(SegHost{H[l - 1] + (size_t)(t + 1) * cap * HID, HID, HID, 0, 0, HID, 1});
+              segs.push_back(SegHost{hprev, HID, HID, 0, 0, HID, 1});
+            }
+            gemm(1 + d, 1, cap, segs, Wl, 64, e, EPI_LSTM, KC_LSTM, 1, l == 0 ? HID : 2 * HID);
+          }
+        }
+        (d == 0 ? hfw : hbw) = H[NLAYER - 1] + (size_t)KL * cap * HID;
+      }
+    }
+
+    // head
+    {
+      float* Wc = reinterpret_cast<float*>(wa.take(std::max<size_t>(fm.head_cnn.size(), 4) * sizeof(float)));
+      float* Wr = reinterpret_cast<float*>(wa.take(std::max<size_t>(fm.head_rnn.size(), 4) * sizeof(float)));
+      if (place) {
+        if (!fm.head_cnn.empty()) DSB_CUDA(cudaMemcpyAsync(Wc, fm.head_cnn.data(), fm.head_cnn.size() * sizeof(float), cudaMemcpyHostToDevice, up_stream));
+        if (!fm.head_rnn.empty()) DSB_CUDA(cudaMemcpyAsync(Wr, fm.head_rnn.data(), fm.head_rnn.size() * sizeof(float), cudaMemcpyHostToDevice, up_stream));
+        DSB_CUDA(cudaStreamSynchronize(up_stream));
+      }
+      Step st;
+      st.kind = ST_HEAD;
+      st.stream = 0;
+      st.head = HeadParams{final_y, final_Lp, fm.L4, hfw, hbw, Wc, Wr, nullptr, nullptr, 0};
+      plan.steps.push_back(st);
+    }
+  }
+};
+
+template <class T>
+void build_plan(dsb_ctx* ctx, ForwardPlan& plan, int64_t cap, cudaStream_t s) {
+  // pass 1: sizes
+  {
+    ForwardPlan scratch;
+    Builder<T> b{ctx, scratch, ctx->model, cap, Arena{}, Arena{}, false, s};
+    b.build();
+    plan.weights.ensure(b.wa.off + 1024);
+    plan.work.ensure(b.ba.off + 1024);
+    plan.work_bytes = b.ba.off + 1024;
+  }
+  DSB_CUDA(cudaMemsetAsync(plan.work.p, 0, plan.work.bytes, s));
+  plan.steps.clear();
+  Arena wa, ba;
+  wa.base = reinterpret_cast<uint8_t*>(plan.weights.p);
+  ba.base = reinterpret_cast<uint8_t*>(plan.work.p);
+  Builder<T> b{ctx, plan, ctx->model, cap, wa, ba, true, s};
+  b.build();
+  DSB_CUDA(cudaStreamSynchronize(s));
+  plan.cap = cap;
+}
+
+struct Timer {       // optional CUDA-event bracket around one launch
+  dsb_ctx* ctx;
+  cudaStream_t s;
+  bool on;
+  Profiler::Rec rec;
+  Timer(dsb_ctx* c, cudaStream_t st, int cls, double flops) : ctx(c), s(st), on(c->prof.enabled) {
+    if (!on) return;
+    rec.a = c->prof.get();
+    rec.b = c->prof.get();
+    rec.cls = cls;
+    rec.flops = flops;
+    cudaEventRecord(rec.a, s);
+  }
+  ~Timer() {
+    if (!on) return;
+    cudaEventRecord(rec.b, s);
+    ctx->prof.recs.push_back(rec);
+  }
+};
+
+template <class T>
+void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, const float* means, const float* stds,
+               const float* lens, const float* signals, float* probs, int32_t* pred, cudaStream_t main_stream) {
+  const FoldedModel& fm = ctx->model;
+  const bool multi = plan.multi_stream && !ctx->prof.enabled && fm.has_rnn() && fm.has_cnn();
+  cudaStream_t streams[3] = {main_stream, multi ? plan.side[0] : main_stream, multi ? plan.side[1] : main_stream};
+  bool forked = false;
+  static const bool debug_sync = getenv("DSB_DEBUG_SYNC") != nullptr;
+  int step_idx = -1;
+  for (const Step& st : plan.steps) {
+    ++step_idx;
+    if (debug_sync && step_idx > 0) {
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) fail(DSB_ERR_CUDA, "step %d (kind %d) failed: %s", step_idx - 1, plan.steps[step_idx - 1].kind, cudaGetErrorString(e));
+    }
+    cudaStream_t s = streams[st.stream];
+    if (multi && !forked && st.kind != ST_FEAT) {
+      // everything after the feature rows may run on the three streams concurrently
+      DSB_CUDA(cudaEventRecord(plan.ev_fork, main_stream));
+      DSB_CUDA(cudaStreamWaitEvent(plan.side[0], plan.ev_fork, 0));
+      DSB_CUDA(cudaStreamWaitEvent(plan.side[1], plan.ev_fork, 0));
+      forked = true;
+    }
+    const int64_t M = n * st.rows_per_sample;
+    switch (st.kind) {
+      case ST_GEMM: {
+        Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
+        if constexpr (std::is_same<T, float>::value) {
+          GemmF32Params g = st.f32;
+          g.epi.M = (int)M;
+          g.rows_valid = (int)M;
+          launch_gemm_f32(g, st.epi_kind, s);
+        } else {
+          launch_gemm_tc(st.tc, (int)M, ctx->sm_count, s);
+        }
+        ctx->launches++;
+        break;
+      }
+      case ST_STEM: {
+        Timer tm(ctx, s, KC_ELEM, 0);
+        StemParams p = st.stem;
+        p.signals = signals;
+        p.n = (int)n;
+        const size_t smem = (size_t)(p.S + 16 + 64 * 7 + 64) * sizeof(float);
+        stem_kernel<T><<<(unsigned)n, 256, smem, s>>>(p);
+        DSB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        break;
+      }
+      case ST_POOL1: {
+        Timer tm(ctx, s, KC_ELEM, 0);
+        const int64_t total = M * (st.C / 8);
+        pool3s1_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), M, st.C);
+        DSB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        break;
+      }
+      case ST_POOL2: {
+        Timer tm(ctx, s, KC_ELEM, 0);
+        const int64_t total = n * st.Lpout * (st.C / 8);
+        pool3s2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), n, st.C,
+                                                                          st.Lin, st.Lpin, st.Lout, st.Lpout, st.pl);
+        DSB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        break;
+      }
+      case ST_FEAT: {
+        Timer tm(ctx, s, KC_ELEM, 0);
+        const int64_t total = n * fm.kmer_len;
+        lstm_feat_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(kmer, means, stds, lens, reinterpret_cast<T*>(plan.F), n, plan.cap,
+                                                                            fm.kmer_len, plan.FW, fm.has_base() ? 1 : 0);
+        DSB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        break;
+      }
+      case ST_ZERO:
+        DSB_CUDA(cudaMemsetAsync(st.dst, 0, st.zero_bytes_per_sample * (size_t)n, s));
+        break;
+      case ST_HEAD: {
+        if (multi) {
+          DSB_CUDA(cudaEventRecord(plan.ev_join[0], plan.side[0]));
+          DSB_CUDA(cudaEventRecord(plan.ev_join[1], plan.side[1]));
+          DSB_CUDA(cudaStreamWaitEvent(main_stream, plan.ev_join[0], 0));
+          DSB_CUDA(cudaStreamWaitEvent(main_stream, plan.ev_join[1], 0));
+        }
+        Timer tm(ctx, s, KC_ELEM, 0);
+        HeadParams p = st.head;
+        p.probs = probs;
+        p.pred = pred;
+        p.n = n;
+        head_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, s>>>(p);
+        DSB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        break;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+size_t forward_workspace_bytes(const dsb_ctx* ctx, int64_t chunk, int precision) {
+  if (!ctx->have_model) return 0;
+  ForwardPlan scratch;
+  size_t bytes = 0;
+  if (precision == DSB_PREC_FP32) {
+    Builder<float> b{const_cast<dsb_ctx*>(ctx), scratch, ctx->model, chunk, Arena{}, Arena{}, false, nullptr};
+    b.build();
+    bytes = b.ba.off + b.wa.off;
+  } else {
+    Builder<__nv_bfloat16> b{const_cast<dsb_ctx*>(ctx), scratch, ctx->model, chunk, Arena{}, Arena{}, false, nullptr};
+    b.build();
+    bytes = b.ba.off + b.wa.off;
+  }
+  return bytes + 2048;
+}
+
+void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, const float* means, const float* stds,
+                 const float* lens, const float* signals, float* probs, int32_t* pred, cudaStream_t stream) {
+  if (!ctx->have_model) fail(DSB_ERR_STATE, "dsb_forward called before dsb_load_weights");
+  if (precision != DSB_PREC_FP32 && precision != DSB_PREC_BF16) fail(DSB_ERR_INVALID, "unknown precision %d", precision);
+  if (n < 0) fail(DSB_ERR_INVALID, "negative sample count");
+  if (n == 0) return;
+  if (!signals || !probs || !pred || (ctx->model.has_rnn() && (!means || !stds || !lens || (ctx->model.has_base() && !kmer))))
+    fail(DSB_ERR_INVALID, "null input/output pointer");
+  if (precision == DSB_PREC_BF16 && ctx->cc_major != 10)
+    fail(DSB_ERR_ARCH, "the bf16 tensor-core path needs an sm_100 device (found sm_%d%d); there is no fallback", ctx->cc_major, ctx->cc_minor);
+  DSB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t want = std::min<int64_t>(ctx->max_chunk, (n + 127) / 128 * 128);
+  auto& slot = ctx->plan[precision];
+  if (!slot || slot->cap < want || slot->cap > ctx->max_chunk) {
+    slot.reset();
+    std::unique_ptr<ForwardPlan, PlanDeleter> np(new ForwardPlan());
+    np->precision = precision;
+    DSB_CUDA(cudaStreamCreateWithFlags(&np->side[0], cudaStreamNonBlocking));
+    DSB_CUDA(cudaStreamCreateWithFlags(&np->side[1], cudaStreamNonBlocking));
+    DSB_CUDA(cudaEventCreateWithFlags(&np->ev_fork, cudaEventDisableTiming));
+    DSB_CUDA(cudaEventCreateWithFlags(&np->ev_join[0], cudaEventDisableTiming));
+    DSB_CUDA(cudaEventCreateWithFlags(&np->ev_join[1], cudaEventDisableTiming));
+    if (precision == DSB_PREC_FP32) build_plan<float>(ctx, *np, want, stream);
+    else build_plan<__nv_bfloat16>(ctx, *np, want, stream);
+    slot = std::move(np);
+  }
+  ForwardPlan& plan = *slot;
+  const int KL = ctx->model.kmer_len, S = ctx->model.signal_len;
+  for (int64_t off = 0; off < n; off += plan.cap) {
+    const int64_t m = std::min<int64_t>(plan.cap, n - off);
+    const int32_t* k = kmer ? kmer + off * KL : nullptr;
+    const float* mu = means ? means + off * KL : nullptr;
+    const float* sd = stds ? stds + off * KL : nullptr;
+    const float* ln = lens ? lens + off * KL : nullptr;
+    if (precision == DSB_PREC_FP32)
+      run_chunk<float>(ctx, plan, m, k, mu, sd, ln, signals + off * S, probs + off * 2, pred + off, stream);
+    else
+      run_chunk<__nv_bfloat16>(ctx, plan, m, k, mu, sd, ln, signals + off * S, probs + off * 2, pred + off, stream);
+  }
+}
+
+}  // namespace dsb

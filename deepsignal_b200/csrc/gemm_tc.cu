@@ -1,0 +1,378 @@
+// gemm_tc.cu — bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands
+// staged by TMA) with the conv / LSTM epilogues fused.  sm_100a only; this is the DSB_PREC_BF16 path.
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0      TMA producer  (one elected lane): A tile [128 x BK] + B tile [BN x BK] per stage
+//   warp 1      TMEM allocator + MMA issuer (one elected lane): BK/16 tcgen05.mma per stage,
+//               tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 16 columns, bias / residual / ReLU / halo-row zeroing
+//               (conv) or the LSTM cell update, bf16 stores
+// Accumulators are double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
+// MMAs of tile i+1.  A-operand "segments" give k-tap convs (row-shifted TMA boxes; out-of-range rows are
+// zero-filled by TMA, sample edges read the zero halo rows) and [x_t | h_{t-1}] for the LSTM.
+#include "gemm_tc.cuh"
+
+namespace dsb {
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int BM_TC = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major smem operand descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
+// Rows are BK*2 bytes (= the swizzle span), 8-row groups are SBO = 8*span bytes apart.
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  constexpr uint32_t span = BK * 2;
+  constexpr uint64_t layout = (span == 128) ? 2ull : 4ull;
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;                              // LBO (unused for swizzled K-major)
+  d |= (uint64_t)((8u * span) >> 4) << 32;             // SBO
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= layout << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int BK, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const int m_tiles, const uint32_t tmem_cols) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.BN;
+  const uint32_t a_bytes = BM_TC * BK * 2, b_bytes = (uint32_t)BN * BK * 2, stage_bytes = a_bytes + b_bytes;
+  const int stages = p.stages;
+  const uint32_t bar_base = smem_base + stages * stage_bytes;   // 8-byte barriers
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  const int n_tiles_n = p.epi.N / BN;
+  const int num_tiles = m_tiles * n_tiles_n;
+  int total_kb = 0;
+  for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = (tile / n_tiles_n) * BM_TC, n0 = (tile % n_tiles_n) * BN;
+        int kb_global = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const SegTC sg = p.seg[s];
+          for (int j = 0; j < sg.nkb; ++j) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), stage_bytes);
+            const uint32_t a_dst = smem_base + stage * stage_bytes;
+            tma_load_2d(a_dst, &maps.a[sg.map], full_bar(stage), sg.col0 + j * BK, row0 + sg.drow);
+            tma_load_2d(a_dst + a_bytes, &maps.b, full_bar(stage), kb_global * BK, n0);
+            ++kb_global;
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      // kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A/B,
+      // N>>3 at bits 17-22, M>>4 at bits 24-28.
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM_TC >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint64_t adesc = make_kmajor_desc<BK>(a_addr);
+          const uint64_t bdesc = make_kmajor_desc<BK>(a_addr + a_bytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(empty_bar(stage));
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;                   // TMEM lane quadrant this warp may access
+    const EpiParams& e = p.epi;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int row = (tile / n_tiles_n) * BM_TC + q * 32 + lane;
+      const int n0 = (tile % n_tiles_n) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const bool row_ok = row < e.M;
+      if constexpr (EPI == EPI_CONV) {
+        const bool halo = e.Lp > 0 && (row % e.Lp) >= e.L;
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t r[16];
+          __syncwarp();
+          tc_ld16(t_row + (uint32_t)c, r);
+          tc_wait_ld();
+          const int col = n0 + c;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col) + i);
+            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + b.x;
+            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b.y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b.z;
+            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b.w;
+          }
+          if (!row_ok) continue;
+          const bool first = col < e.split;
+          if (e.res != nullptr && first) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.res) + (size_t)row * e.res_ld + e.res_c0 + col);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 rv = __ldg(rp + h);
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                v[8 * h + 2 * i] += __uint_as_float(w[i] << 16);
+                v[8 * h + 2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+              }
+            }
+          }
+          if ((e.relu_mask >> (col >> 4)) & 1u) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (halo) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
+          __nv_bfloat16* dst = first ? reinterpret_cast<__nv_bfloat16*>(e.d0) + (size_t)row * e.ld0 + e.c0 + col
+                                     : reinterpret_cast<__nv_bfloat16*>(e.d1) + (size_t)row * e.ld1 + e.c1 + col - e.split;
+          uint4* dp = reinterpret_cast<uint4*>(dst);
+          dp[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          dp[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        }
+      } else {
+        // LSTM: columns 4*u+g.  64 columns (16 hidden units) per iteration.
+        for (int c = 0; c < BN; c += 64) {
+          uint32_t r[4][16];
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tc_ld16(t_row + (uint32_t)(c + 16 * i), r[i]);
+          tc_wait_ld();
+          if (!row_ok) continue;
+          const int col = n0 + c;
+          const int u0 = col >> 2;
+          float* cp = e.c + (size_t)row * HID + u0;
+          float hn[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 cprev = *reinterpret_cast<const float4*>(cp + 4 * i);
+            const float cpv[4] = {cprev.x, cprev.y, cprev.z, cprev.w};
+            float cn[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col + 16 * i + 4 * j));
+              lstm_unit<true>(__uint_as_float(r[i][4 * j + 0]) + b.x, __uint_as_float(r[i][4 * j + 1]) + b.y,
+                              __uint_as_float(r[i][4 * j + 2]) + b.z, __uint_as_float(r[i][4 * j + 3]) + b.w,
+                              cpv[j], cn[j], hn[4 * i + j]);
+            }
+            *reinterpret_cast<float4*>(cp + 4 * i) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          }
+          uint4* hp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.h_out) + (size_t)row * HID + u0);
+          hp[0] = make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]), pack_bf16(hn[6], hn[7]));
+          hp[1] = make_uint4(pack_bf16(hn[8], hn[9]), pack_bf16(hn[10], hn[11]), pack_bf16(hn[12], hn[13]), pack_bf16(hn[14], hn[15]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  DSB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || sym == nullptr) fail(DSB_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+template <int BK, int EPI>
+void launch_one(const TcLaunch& L, int m_tiles, int grid, uint32_t tmem_cols, cudaStream_t s) {
+  auto kern = gemm_tc_kernel<BK, EPI>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  DSB_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[dev & 63] = true;
+  }
+  kern<<<grid, TC_THREADS, L.smem, s>>>(L.maps, L.p, m_tiles, tmem_cols);
+  DSB_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+void encode_map_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                     int box_rows, int box_cols) {
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = (box_cols * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : (box_cols * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (sw == CU_TENSOR_MAP_SWIZZLE_NONE) fail(DSB_ERR_INVALID, "tensor map box must span 64 or 128 bytes");
+  if (((uintptr_t)base & 15) || ((ld * 2) & 15)) fail(DSB_ERR_INVALID, "tensor map base/stride must be 16-byte aligned");
+  CUresult r = get_encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(DSB_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld box=%dx%d)",
+                              (int)r, (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);
+}
+
+void finalize_tc_launch(TcLaunch& L) {
+  const size_t stage_bytes = (size_t)(BM_TC + L.p.BN) * L.BK * 2;
+  int total_kb = 0;
+  for (int s = 0; s < L.p.nseg; ++s) total_kb += L.p.seg[s].nkb;
+  const size_t budget = 200 * 1024;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  L.p.stages = stages;
+  size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16;
+  // 2*BN TMEM columns per CTA: keep co-resident CTAs within the 512-column budget
+  const int cols = 2 * L.p.BN;
+  if (cols > 256 && smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM
+  else if (cols > 128 && smem < 80 * 1024) smem = 80 * 1024;   // at most two
+  L.smem = smem;
+  if (L.p.BN % 16 != 0 || L.p.BN < 16 || L.p.BN > 256 || L.p.epi.N % L.p.BN != 0)
+    fail(DSB_ERR_INVALID, "bad GEMM tile: N=%d BN=%d", L.p.epi.N, L.p.BN);
+}
+
+void launch_gemm_tc(const TcLaunch& L, int M, int sm_count, cudaStream_t s) {
+  const int m_tiles = (M + BM_TC - 1) / BM_TC;
+  const int num_tiles = m_tiles * (L.p.epi.N / L.p.BN);
+  const int grid = num_tiles < sm_count ? num_tiles : sm_count;
+  if (grid <= 0) return;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * L.p.BN)) cols <<= 1;
+  TcLaunch Lr = L;
+  Lr.p.epi.M = M;
+  if (L.BK == 64) {
+    if (L.epi_kind == EPI_CONV) launch_one<64, EPI_CONV>(Lr, m_tiles, grid, cols, s);
+    else launch_one<64, EPI_LSTM>(Lr, m_tiles, grid, cols, s);
+  } else {
+    if (L.epi_kind == EPI_CONV) launch_one<32, EPI_CONV>(Lr, m_tiles, grid, cols, s);
+    else fail(DSB_ERR_INVALID, "LSTM epilogue needs BK=64");
+  }
+}
+
+}  // namespace dsb

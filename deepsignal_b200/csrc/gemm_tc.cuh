@@ -1,0 +1,43 @@
+// gemm_tc.cuh — interface of the tcgen05 / TMA bf16 GEMM (sm_100a only).
+#pragma once
+#include "ops.cuh"
+
+namespace dsb {
+
+struct SegTC {            // one A segment: K blocks read through tensor map `map`
+  int map;                // index into TcMaps::a
+  int col0;               // first column (elements) in the mapped matrix
+  int drow;               // row shift (conv tap - pad)
+  int nkb;                // number of BK-wide K blocks
+};
+
+struct alignas(64) TcMaps {
+  CUtensorMap a[2];
+  CUtensorMap b;
+};
+
+struct GemmTCParams {
+  int nseg = 0;
+  SegTC seg[MAX_SEG];
+  int BN = 0;             // N tile (multiple of 16, <= 256, divides epi.N)
+  int stages = 0;
+  EpiParams epi;
+};
+
+struct TcLaunch {         // everything needed to launch one prebuilt GEMM
+  TcMaps maps;
+  GemmTCParams p;
+  int BK = 64;            // 64 -> SWIZZLE_128B tiles, 32 -> SWIZZLE_64B tiles
+  int epi_kind = EPI_CONV;
+  size_t smem = 0;
+  double flops_per_row = 0;
+};
+
+// Encode a 2-D bf16 row-major [rows][cols] (leading dimension ld elements) tensor map with a
+// [box_rows][box_cols] box; box_cols*2 bytes must equal the swizzle span (128 or 64).
+void encode_map_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                     int box_rows, int box_cols);
+void finalize_tc_launch(TcLaunch& L);                       // picks stages / smem
+void launch_gemm_tc(const TcLaunch& L, int M, int sm_count, cudaStream_t s);
+
+}  // namespace dsb

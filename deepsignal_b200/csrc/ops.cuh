@@ -1,0 +1,80 @@
+// ops.cuh — the GEMM-with-epilogue "op" both forward backends execute, and shared device math.
+//
+// Every heavy layer of the call_mods graph is expressed as
+//     D[M, N] = epilogue( sum_s  A_s[row + drow_s, col0_s : col0_s + K_s] · B[:, koff_s : koff_s + K_s]^T )
+// where the A "segments" cover 1x1 convs (one segment), k-tap convs (one segment per tap, drow = tap - pad,
+// reading the zero halo rows of the padded row layout at sample edges) and LSTM steps (x_t | h_{t-1}).
+#pragma once
+#include "common.cuh"
+
+namespace dsb {
+
+constexpr int MAX_SEG = 5;
+
+enum EpiKind { EPI_CONV = 0, EPI_LSTM = 1 };
+
+struct EpiParams {
+  int M = 0;              // valid rows
+  int N = 0;              // output columns, multiple of 16
+  const float* bias = nullptr;
+  // EPI_CONV: columns [0, split) -> d0[:, c0 + col], columns [split, N) -> d1[:, c1 + col - split]
+  void* d0 = nullptr; int ld0 = 0; int c0 = 0;
+  void* d1 = nullptr; int ld1 = 0; int c1 = 0;
+  int split = 0;
+  uint32_t relu_mask = 0; // bit j: ReLU on columns [16j, 16j+16)
+  const void* res = nullptr; int res_ld = 0; int res_c0 = 0;   // residual added before ReLU (d0 columns)
+  int Lp = 0, L = 0;      // padded row layout: rows with (row % Lp) >= L are written as zero
+  // EPI_LSTM: columns are 4*u+g; c [M][256] fp32 updated in place, h_out [M][256]
+  float* c = nullptr;
+  void* h_out = nullptr;
+};
+
+struct SegF32 {           // fp32 backend: plain pointers
+  const float* a; int ld; int col0; int drow; int K;
+};
+
+struct GemmF32Params {
+  int nseg;
+  SegF32 seg[MAX_SEG];
+  int rows_valid;         // A rows outside [0, rows_valid) read as zero
+  const float* B;         // [N][Ktot] K-major
+  int Ktot;
+  EpiParams epi;
+};
+
+template <class T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <class T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// exact-ish activations for the fp32 path, MUFU-based ones for the bf16 path
+template <bool FAST> __device__ __forceinline__ float act_tanh(float x) {
+  if constexpr (FAST) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  } else {
+    return tanhf(x);
+  }
+}
+template <bool FAST> __device__ __forceinline__ float act_sigmoid(float x) {
+  if constexpr (FAST) {
+    return fmaf(act_tanh<true>(0.5f * x), 0.5f, 0.5f);
+  } else {
+    return 1.0f / (1.0f + expf(-x));
+  }
+}
+
+// LSTMCell step for one hidden unit (reference layers.py:49-50; tf LSTMCell, forget_bias = 1.0)
+template <bool FAST>
+__device__ __forceinline__ void lstm_unit(float zi, float zj, float zf, float zo, float c_prev, float& c_new, float& h_new) {
+  c_new = act_sigmoid<FAST>(zf + 1.0f) * c_prev + act_sigmoid<FAST>(zi) * act_tanh<FAST>(zj);
+  h_new = act_sigmoid<FAST>(zo) * act_tanh<FAST>(c_new);
+}
+
+// ---- launch helpers implemented in the .cu files -------------------------------------------------
+void launch_gemm_f32(const GemmF32Params& p, int epi_kind, cudaStream_t s);
+
+}  // namespace dsb

@@ -1,0 +1,183 @@
+/*
+ * dsb200.h — C ABI of libdsb200.so: the B200-native (sm_100a) implementation of
+ * deepsignal's call_mods hot path.
+ *
+ * The reference (bioinfomaticsCSU/deepsignal v0.2.0) has no FFI / plugin API; the
+ * boundary this library replaces is two Python call sites:
+ *
+ *   forward     deepsignal/call_modifications.py:168-178  (sess.run inside _call_mods,
+ *               graph = deepsignal/model.py:25-108 + deepsignal/layers.py:20-264)
+ *   extraction  deepsignal/extract_features.py:215-286    (_extract_features per-read math:
+ *               :211-212 rescale, :143-151 normalise, :154-190 window, :254-276 site loop;
+ *               motif scan deepsignal/utils/process_utils.py:95-110)
+ *
+ * Conventions
+ *  - plain C, no C++ exceptions cross the ABI; every function returns 0 on success or a
+ *    negative dsb_status; dsb_last_error(ctx) gives the message.
+ *  - one dsb_ctx per GPU; a ctx is not thread-safe, independent ctxs are.
+ *  - "_dev" entry points take DEVICE pointers owned by the caller and are asynchronous on
+ *    the given cudaStream_t (passed as void*; NULL = legacy default stream).  "_host" entry
+ *    points take HOST pointers, stage through pinned buffers, and return after the results
+ *    are on the host.  The library never frees caller memory.
+ *  - there is no CPU fallback and no backend dispatch: without a CUDA device (or with a
+ *    non-sm_100 device for the tensor-core path) calls fail with DSB_ERR_CUDA / DSB_ERR_ARCH.
+ */
+#ifndef DSB200_H_
+#define DSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DSB_API __attribute__((visibility("default")))
+#else
+#define DSB_API
+#endif
+
+typedef struct dsb_ctx dsb_ctx;
+
+typedef enum dsb_status {
+  DSB_OK = 0,
+  DSB_ERR_INVALID = -1,   /* bad argument                                  */
+  DSB_ERR_CUDA = -2,      /* CUDA runtime / driver error                   */
+  DSB_ERR_WEIGHTS = -3,   /* missing / mis-shaped checkpoint tensor        */
+  DSB_ERR_STATE = -4,     /* e.g. forward before load_weights              */
+  DSB_ERR_CAPACITY = -5,  /* caller-provided output capacity too small     */
+  DSB_ERR_ARCH = -6,      /* tensor-core path needs an sm_100 device       */
+  DSB_ERR_NOMEM = -7
+} dsb_status;
+
+/* model-variant and precision flags of dsb_load_weights (reference flags --is_cnn/--is_rnn/
+ * --is_base, deepsignal/deepsignal.py:246-257; model.py:59-95) */
+#define DSB_FLAG_CNN 1u
+#define DSB_FLAG_RNN 2u
+#define DSB_FLAG_BASE 4u
+#define DSB_FLAG_DEFAULT (DSB_FLAG_CNN | DSB_FLAG_RNN | DSB_FLAG_BASE)
+
+typedef enum dsb_precision {
+  DSB_PREC_FP32 = 0,      /* CUDA-core fp32 path, 1e-4 abs parity target   */
+  DSB_PREC_BF16 = 1       /* tcgen05 bf16 path (fp32 accumulate), 2e-3 abs */
+} dsb_precision;
+
+/* One checkpoint tensor, host float32, keyed by its TF-1.x variable name (the names a
+ * tf.train.Saver bundle of the reference model holds; restore site
+ * call_modifications.py:210-211).  The library copies and folds; caller keeps ownership. */
+typedef struct dsb_tensor {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} dsb_tensor;
+
+/* ---- context -------------------------------------------------------------------------- */
+DSB_API int dsb_abi_version(void);
+DSB_API int dsb_create(int device, dsb_ctx** out);
+DSB_API int dsb_destroy(dsb_ctx* ctx);
+DSB_API const char* dsb_last_error(const dsb_ctx* ctx);   /* ctx may be NULL: last create error */
+
+/* ---- model: replaces Model(...) + Saver.restore + sess.run ------------------------------ */
+/* kmer_len / signal_len: reference --kmer_len / --cent_signals_len (17 / 360). */
+DSB_API int dsb_load_weights(dsb_ctx* ctx, const dsb_tensor* tensors, int32_t n_tensors,
+                     uint32_t flags, int32_t kmer_len, int32_t signal_len);
+
+/* Largest number of samples processed per internal pass (workspace grows with it). */
+DSB_API int dsb_set_max_chunk(dsb_ctx* ctx, int64_t max_chunk);
+DSB_API size_t dsb_workspace_bytes(const dsb_ctx* ctx, int64_t n, int32_t precision);
+
+/* Forward of n samples (the feed_dict / fetches of call_modifications.py:168-178):
+ *   kmer    int32 [n, kmer_len]   base codes 0..4 (A C G T N)      -> model.base_int
+ *   means   f32   [n, kmer_len]                                     -> model.means
+ *   stds    f32   [n, kmer_len]                                     -> model.stds
+ *   lens    f32   [n, kmer_len]   signal counts per base            -> model.sanums
+ *   signals f32   [n, signal_len]                                   -> model.signals
+ *   probs   f32   [n, 2]          sigmoid(logits) = model.activation_logits
+ *   pred    int32 [n]             argmax(probs), ties -> 0 = model.prediction
+ */
+DSB_API int dsb_forward_dev(dsb_ctx* ctx, int32_t precision, int64_t n,
+                    const int32_t* kmer, const float* means, const float* stds, const float* lens,
+                    const float* signals, float* probs, int32_t* pred, void* cuda_stream);
+DSB_API int dsb_forward_host(dsb_ctx* ctx, int32_t precision, int64_t n,
+                     const int32_t* kmer, const float* means, const float* stds, const float* lens,
+                     const float* signals, float* probs, int32_t* pred);
+
+/* Per-kernel-class timing of the most recent profiled forward (CUDA events on the launch
+ * stream around every launch of the class).  classes: 0 gemm, 1 lstm-gemm, 2 elementwise. */
+DSB_API int dsb_set_profiling(dsb_ctx* ctx, int32_t enabled);
+DSB_API int dsb_get_profile(dsb_ctx* ctx, int32_t cls, double* ms_total, int64_t* launches, double* flops);
+DSB_API int64_t dsb_launch_count(const dsb_ctx* ctx);   /* kernels launched by this ctx so far */
+
+/* ---- feature extraction: replaces the math of _extract_features ---------------------------- */
+typedef struct dsb_reads {
+  int64_t n_reads;
+  const int16_t* raw;          /* [raw_off[n_reads]] concatenated Raw/Reads/ * /Signal         */
+  const int64_t* raw_off;      /* [n_reads+1]                                                  */
+  const double* scaling;       /* [n_reads] range / digitisation (extract_features.py:198-201) */
+  const double* offset;        /* [n_reads] channel offset                                     */
+  const int32_t* ev_start;     /* [ev_off[n_reads]] Events.start + read_start_rel_to_raw        */
+  const int32_t* ev_len;       /* Events.length                                                */
+  const uint8_t* ev_base;      /* Events.base (ASCII)                                          */
+  const int64_t* ev_off;       /* [n_reads+1]                                                  */
+  const int64_t* chrom_start;  /* [n_reads] Alignment.mapped_start                             */
+  const uint8_t* strand_minus; /* [n_reads] 1 if Alignment.mapped_strand == '-'                */
+  const int64_t* chrom_len;    /* [n_reads] contig length, -1 without --reference_path         */
+} dsb_reads;
+
+typedef struct dsb_extract_params {
+  int32_t kmer_len;            /* odd, <= 33 (default 17)                                      */
+  int32_t signal_len;          /* default 360                                                  */
+  int32_t normalize_method;    /* 0 = mad, 1 = zscore  (--normalize_method)                    */
+  int32_t mod_loc;             /* --mod_loc                                                    */
+  int32_t n_motifs;            /* expanded motif sequences, all of motif_len                   */
+  int32_t motif_len;           /* <= 16                                                        */
+  const char* motifs;          /* HOST pointer, n_motifs * motif_len ASCII bytes               */
+} dsb_extract_params;
+
+/* Caller-allocated per-site outputs, `capacity` sites each; any pointer may be NULL to skip
+ * that output.  Sites are ordered by read, then by location in the read. */
+typedef struct dsb_sites {
+  int64_t capacity;
+  int32_t* site_read;          /* [cap]      index of the read                                  */
+  int32_t* site_loc;           /* [cap]      loc_in_read                                        */
+  int64_t* pos;                /* [cap]      extract_features.py:255-260                        */
+  int64_t* pos_in_strand;      /* [cap]                                                         */
+  int32_t* kmer;               /* [cap, k]   base codes (model.base_int); 255 = not ACGTN       */
+  float* means;                /* [cap, k]   float32 cast of the float64 means (model feed)     */
+  float* stds;                 /* [cap, k]                                                      */
+  float* lens;                 /* [cap, k]   slice lengths as float32 (model.sanums)            */
+  float* signals;              /* [cap, signal_len]                                             */
+  double* means64;             /* [cap, k]   float64, for the feature-file text                 */
+  double* stds64;              /* [cap, k]                                                      */
+  int32_t* lens_i32;           /* [cap, k]                                                      */
+  double* signals64;           /* [cap, signal_len]                                             */
+  int32_t* window;             /* [cap, 3]   mode (0 short / 1 centre subsample / 2 window), start, n_real */
+} dsb_sites;
+
+/* All array pointers in `reads` and `sites` are DEVICE pointers.  n_sites (HOST pointer) gets the
+ * number of sites found; if it exceeds sites->capacity the call returns DSB_ERR_CAPACITY after
+ * writing the first `capacity` sites.  read_shift / read_scale (device, [n_reads], may be NULL)
+ * receive the per-read normalisation constants.  Synchronises the stream once (site count). */
+DSB_API int dsb_extract_dev(dsb_ctx* ctx, const dsb_reads* reads, const dsb_extract_params* params,
+                    const dsb_sites* sites, int64_t* n_sites, double* read_shift, double* read_scale,
+                    void* cuda_stream);
+/* Same with HOST pointers everywhere (stages through device buffers owned by the ctx). */
+DSB_API int dsb_extract_host(dsb_ctx* ctx, const dsb_reads* reads, const dsb_extract_params* params,
+                     const dsb_sites* sites, int64_t* n_sites, double* read_shift, double* read_scale);
+/* Upper bound on the number of sites of a read batch (= number of events), for sizing. */
+DSB_API int64_t dsb_extract_max_sites(const dsb_reads* reads_host_offsets_only);
+
+/* ---- fused end-to-end: extraction straight into the forward (fast5 -> call mode,
+ *      call_modifications.py:94-122,264-278), features never leave HBM ------------------------ */
+DSB_API int dsb_extract_call_dev(dsb_ctx* ctx, int32_t precision, const dsb_reads* reads,
+                         const dsb_extract_params* params, const dsb_sites* sites, int64_t* n_sites,
+                         float* probs, int32_t* pred, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSB200_H_ */

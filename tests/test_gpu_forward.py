@@ -1,0 +1,164 @@
+"""GPU parity of the call_mods forward (dsb_forward_* through the C ABI) against the float64 oracle.
+
+Tolerances are BASELINE.json's: probabilities within 1e-4 abs on the fp32 path, within 2e-3 abs on
+the bf16 tensor-core path with >= 99.9 % identical binary calls."""
+import numpy as np
+import pytest
+
+from deepsignal_b200 import weights as W
+from deepsignal_b200.synth import synth_features
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-3
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from deepsignal_b200.engine import Engine
+    eng = Engine(0)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def ckpt():
+    return W.random_checkpoint(17, "stress")
+
+
+def _inputs(n, seed):
+    f = synth_features(n, seed=seed)
+    return f["kmer"], f["means"], f["stds"], f["lens"].astype(np.float32), f["signals"]
+
+
+def _report(tag, got, ref, pred, ref_pred):
+    err = np.abs(got - ref)
+    margin = np.abs(ref[:, 0] - ref[:, 1])
+    flips = pred != ref_pred
+    print("\n[{}] n={} max|dp|={:.3e} mean|dp|={:.3e} flips={} (margins of flips: {})".format(
+        tag, len(got), err.max(), err.mean(), int(flips.sum()), np.round(margin[flips], 5).tolist()[:8]))
+    return err, flips, margin
+
+
+def test_fp32_matches_oracle(engine, ckpt):
+    engine.load_weights(ckpt)
+    x = _inputs(300, 101)
+    ref, ref_pred = mo.forward(ckpt, *x)
+    got, pred = engine.forward(*x, precision="fp32")
+    err, flips, margin = _report("fp32", got, ref, pred, ref_pred)
+    assert err.max() <= FP32_TOL
+    assert not np.any(flips & (margin > 2 * FP32_TOL))
+
+
+def test_bf16_matches_oracle(engine, ckpt):
+    engine.load_weights(ckpt)
+    x = _inputs(2048, 102)
+    ref, ref_pred = mo.forward(ckpt, *x)
+    got, pred = engine.forward(*x, precision="bf16")
+    err, flips, margin = _report("bf16", got, ref, pred, ref_pred)
+    assert err.max() <= BF16_TOL
+    assert flips.mean() <= 1e-3
+    assert not np.any(flips & (margin > 2 * BF16_TOL))
+
+
+def test_bf16_tracks_fp32_on_device(engine, ckpt):
+    engine.load_weights(ckpt)
+    x = _inputs(5000, 103)
+    a, pa = engine.forward(*x, precision="fp32")
+    b, pb = engine.forward(*x, precision="bf16")
+    print("\n[bf16 vs fp32] max|dp|={:.3e} flips={}".format(np.abs(a - b).max(), int((pa != pb).sum())))
+    assert np.abs(a - b).max() <= BF16_TOL
+    assert (pa != pb).mean() <= 1e-3
+
+
+@pytest.mark.parametrize("kw", [dict(is_cnn=False), dict(is_rnn=False), dict(is_base=False)])
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_model_variants(engine, kw, precision, tol):
+    ck = W.random_checkpoint(23, "stress", **kw)
+    engine.load_weights(ck, **kw)
+    x = _inputs(130, 104)
+    ref, _ = mo.forward(ck, *x, **kw)
+    got, _ = engine.forward(*x, precision=precision)
+    assert np.abs(got - ref).max() <= tol
+
+
+def test_tf_default_checkpoint(engine):
+    ck = W.random_checkpoint(17, "tf_default")
+    engine.load_weights(ck)
+    x = _inputs(256, 105)
+    ref, _ = mo.forward(ck, *x)
+    for precision, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL)):
+        got, _ = engine.forward(*x, precision=precision)
+        assert np.abs(got - ref).max() <= tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_chunking_and_ragged_sizes_are_batch_invariant(engine, ckpt, precision):
+    engine.load_weights(ckpt)
+    x = _inputs(1000, 106)
+    engine.set_max_chunk(8192)
+    full, pfull = engine.forward(*x, precision=precision)
+    engine.set_max_chunk(256)
+    chunked, pch = engine.forward(*x, precision=precision)
+    assert np.array_equal(full, chunked) and np.array_equal(pfull, pch)
+    for n in (1, 7, 127, 129):
+        part, _ = engine.forward(*[a[:n] for a in x], precision=precision)
+        assert np.array_equal(part, full[:n]), n
+    engine.set_max_chunk(8192)
+    empty, pe = engine.forward(*[a[:0] for a in x], precision=precision)
+    assert empty.shape == (0, 2) and pe.shape == (0,)
+
+
+def test_device_pointer_entry_matches_host_entry(engine, ckpt):
+    import torch
+    engine.load_weights(ckpt)
+    x = _inputs(700, 107)
+    host, hp = engine.forward(*x, precision="bf16")
+    dev = [torch.from_numpy(a).cuda() for a in x]
+    probs, pred = engine.forward_torch(*dev, precision="bf16")
+    torch.cuda.synchronize()
+    assert np.array_equal(probs.cpu().numpy(), host) and np.array_equal(pred.cpu().numpy(), hp)
+
+
+def test_large_batch_properties(engine, ckpt):
+    """Full-size property check (no oracle): a 262,144-sample device-resident batch is permutation
+    equivariant and its head equals the same samples computed alone."""
+    import torch
+    engine.load_weights(ckpt)
+    n = 262144
+    base = _inputs(4096, 108)
+    rep = n // 4096
+    g = torch.Generator().manual_seed(1)
+    perm = torch.randperm(n, generator=g)
+    dev = [torch.from_numpy(np.tile(a, (rep, 1))).cuda() for a in base]
+    p1, c1 = engine.forward_torch(*dev, precision="bf16")
+    dev2 = [t[perm.cuda()].contiguous() for t in dev]
+    p2, c2 = engine.forward_torch(*dev2, precision="bf16")
+    torch.cuda.synchronize()
+    assert torch.equal(p1[perm.cuda()], p2) and torch.equal(c1[perm.cuda()], c2)
+    small, _ = engine.forward(*base, precision="bf16")
+    assert np.array_equal(p1[:4096].cpu().numpy(), small)
+    assert torch.equal(p1[:4096], p1[4096:8192])
+
+
+def test_errors(engine, ckpt):
+    from deepsignal_b200._lib import DsbError
+    from deepsignal_b200.engine import Engine
+    e2 = Engine(0)
+    x = _inputs(4, 109)
+    e2.kmer_len, e2.signal_len = 17, 360
+    with pytest.raises(DsbError):
+        e2.forward(*x)                      # forward before load_weights
+    bad = dict(ckpt)
+    bad.pop("dense/kernel")
+    with pytest.raises(DsbError):
+        e2.load_weights(bad)
+    bad = dict(ckpt)
+    bad["modelembedding"] = np.zeros((10, 128), np.float32)
+    with pytest.raises(DsbError):
+        e2.load_weights(bad)
+    with pytest.raises(DsbError):
+        e2.load_weights(ckpt, is_cnn=False, is_rnn=False)
+    e2.close()
