@@ -11,8 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libdsb200.so")
 DSB_OK = 0
 DSB_ERR_CAPACITY = -5
 FLAG_CNN, FLAG_RNN, FLAG_BASE = 1, 2, 4
-PREC_FP32, PREC_BF16 = 0, 1
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, 0: PREC_FP32, 1: PREC_BF16}
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, 0: PREC_FP32, 1: PREC_BF16, 2: PREC_FP16}
 
 EXPORTS = [
     "dsb_abi_version", "dsb_create", "dsb_destroy", "dsb_last_error", "dsb_load_weights",

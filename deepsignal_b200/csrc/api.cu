@@ -68,8 +68,7 @@ int dsb_destroy(dsb_ctx* ctx) {
   if (!ctx) return DSB_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  ctx->plan[0].reset();
-  ctx->plan[1].reset();
+  for (auto& p : ctx->plan) p.reset();
   ctx->xw.reset();
   for (cudaStream_t s : {ctx->stream_h2d, ctx->stream_compute, ctx->stream_d2h}) if (s) cudaStreamDestroy(s);
   for (int i = 0; i < 2; ++i) {
@@ -88,8 +87,7 @@ int dsb_load_weights(dsb_ctx* ctx, const dsb_tensor* tensors, int32_t n_tensors,
   return guarded(ctx, [&] {
     if (!tensors || n_tensors <= 0) dsb::fail(DSB_ERR_INVALID, "no tensors given");
     ctx->have_model = false;
-    ctx->plan[0].reset();
-    ctx->plan[1].reset();
+    for (auto& p : ctx->plan) p.reset();
     dsb::fold_model(tensors, n_tensors, flags, kmer_len, signal_len, ctx->model);
     ctx->have_model = true;
   });

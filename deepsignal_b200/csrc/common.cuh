@@ -175,7 +175,7 @@ struct dsb_ctx {
   bool have_model = false;
   dsb::FoldedModel model;
   dsb::Profiler prof;
-  std::unique_ptr<dsb::ForwardPlan, dsb::PlanDeleter> plan[2];   // per precision
+  std::unique_ptr<dsb::ForwardPlan, dsb::PlanDeleter> plan[3];   // per precision
   std::unique_ptr<dsb::ExtractWork, dsb::ExtractDeleter> xw;
   // staging for the _host entry points
   dsb::DevBuf stage_in[2], stage_out[2];

@@ -46,6 +46,31 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 
+template <> struct Vec8<__half> {
+  float v[8];
+  __device__ __forceinline__ static Vec8 load(const __half* p) {
+    Vec8 r;
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      r.v[2 * i] = f.x;
+      r.v[2 * i + 1] = f.y;
+    }
+    return r;
+  }
+  __device__ __forceinline__ void store(__half* p) const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
 // ---- stem: signals [n][S] fp32 -> P1 [n*Lp2][64] --------------------------------------------------
 // conv 1x7 stride 2 SAME (1->64) + folded BN + ReLU at L1 positions, then maxpool 1x3 stride 2 SAME
 // (reference layers.py:183-191).  One CTA per sample, 256 threads; thread -> (channel, position stripe).

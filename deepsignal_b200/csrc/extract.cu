@@ -207,29 +207,44 @@ __global__ void __launch_bounds__(NORM_THREADS) read_norm_kernel(const NormParam
 }
 
 // numpy's pairwise summation (DOUBLE_pairwise_sum): < 8 sequential, <= 128 eight-way unrolled, else halves.
-template <class F> __device__ double pairwise_sum(const F& f, int a0, int n) {
+template <class F> __device__ double pairwise_block(const F& f, int a0, int n) {
   if (n < 8) {
     double res = 0.0;
     for (int i = 0; i < n; ++i) res = __dadd_rn(res, f(a0 + i));
     return res;
   }
-  if (n <= 128) {
-    double r[8];
+  double r[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = f(a0 + j);
-    int i = 8;
-    for (; i < n - (n % 8); i += 8) {
+  for (int j = 0; j < 8; ++j) r[j] = f(a0 + j);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(a0 + i + j));
-    }
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; i < n; ++i) res = __dadd_rn(res, f(a0 + i));
-    return res;
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(a0 + i + j));
   }
-  int n2 = n / 2;
-  n2 -= n2 % 8;
-  return __dadd_rn(pairwise_sum(f, a0, n2), pairwise_sum(f, a0 + n2, n - n2));
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, f(a0 + i));
+  return res;
+}
+// The n > 128 recursion of numpy (split at n/2 rounded down to a multiple of 8) with an explicit stack.
+template <class F> __device__ double pairwise_sum(const F& f, int a0, int n) {
+  if (n <= 128) return pairwise_block(f, a0, n);
+  struct Frame { int a0, n, state; double left; };
+  Frame st[26];
+  int sp = 0;
+  st[0] = Frame{a0, n, 0, 0.0};
+  double ret = 0.0;
+  while (sp >= 0) {
+    Frame& fr = st[sp];
+    if (fr.n <= 128) { ret = pairwise_block(f, fr.a0, fr.n); --sp; continue; }
+    int n2 = fr.n / 2;
+    n2 -= n2 % 8;
+    if (fr.state == 0) { fr.state = 1; st[sp + 1] = Frame{fr.a0, n2, 0, 0.0}; ++sp; continue; }
+    if (fr.state == 1) { fr.left = ret; fr.state = 2; st[sp + 1] = Frame{fr.a0 + n2, fr.n - n2, 0, 0.0}; ++sp; continue; }
+    ret = __dadd_rn(fr.left, ret);
+    --sp;
+  }
+  return ret;
 }
 
 __device__ __forceinline__ int find_read(const int64_t* off, int64_t R, int64_t e) {

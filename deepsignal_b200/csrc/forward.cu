@@ -90,6 +90,7 @@ DevGemm<T> upload_gemm(Arena& wa, const FoldedGemm& g, const std::vector<std::ar
         for (int k = 0; k < p[2]; ++k) {
           const float v = (k < p[1]) ? g.w[(size_t)n * g.K + p[0] + k] : 0.f;
           if constexpr (std::is_same<T, float>::value) h[(size_t)n * Ktot + ko + k] = v;
+          else if constexpr (std::is_same<T, __half>::value) h[(size_t)n * Ktot + ko + k] = __float2half_rn(v);
           else h[(size_t)n * Ktot + ko + k] = __float2bfloat16_rn(v);
         }
         ko += p[2];
@@ -147,6 +148,7 @@ struct Builder {
       TcLaunch& L = st.tc;
       L.BK = BK;
       L.epi_kind = epi_kind;
+      L.fp16 = std::is_same<T, __half>::value;
       L.p.nseg = (int)segs.size();
       const void* map_base[2] = {nullptr, nullptr};
       int nmaps = 0, kt = 0;
@@ -157,7 +159,7 @@ struct Builder {
           if (nmaps == 2) fail(DSB_ERR_STATE, "internal: more than two A matrices in one GEMM");
           mi = nmaps++;
           map_base[mi] = segs[i].a;
-          encode_map_bf16(&L.maps.a[mi], segs[i].a, rows_cap, segs[i].cols, segs[i].ld, 128, BK);
+          encode_map_16(&L.maps.a[mi], segs[i].a, rows_cap, segs[i].cols, segs[i].ld, 128, BK, std::is_same<T, __half>::value);
         }
         const int nkb = round_up(segs[i].K, BK) / BK;
         L.p.seg[i] = SegTC{mi, segs[i].col0, segs[i].drow, nkb};
@@ -166,7 +168,7 @@ struct Builder {
       if (nmaps == 1) L.maps.a[1] = L.maps.a[0];
       if (kt != W.Ktot) fail(DSB_ERR_STATE, "internal: bf16 GEMM K mismatch %d vs %d", kt, W.Ktot);
       L.p.BN = W.N <= 256 ? W.N : 256;
-      encode_map_bf16(&L.maps.b, W.w, W.N, W.Ktot, W.Ktot, L.p.BN, BK);
+      encode_map_16(&L.maps.b, W.w, W.N, W.Ktot, W.Ktot, L.p.BN, BK, std::is_same<T, __half>::value);
       L.p.epi = epi;
       L.flops_per_row = st.flops_per_row;
       finalize_tc_launch(L);
@@ -519,6 +521,10 @@ size_t forward_workspace_bytes(const dsb_ctx* ctx, int64_t chunk, int precision)
     Builder<float> b{const_cast<dsb_ctx*>(ctx), scratch, ctx->model, chunk, Arena{}, Arena{}, false, nullptr};
     b.build();
     bytes = b.ba.off + b.wa.off;
+  } else if (precision == DSB_PREC_FP16) {
+    Builder<__half> b{const_cast<dsb_ctx*>(ctx), scratch, ctx->model, chunk, Arena{}, Arena{}, false, nullptr};
+    b.build();
+    bytes = b.ba.off + b.wa.off;
   } else {
     Builder<__nv_bfloat16> b{const_cast<dsb_ctx*>(ctx), scratch, ctx->model, chunk, Arena{}, Arena{}, false, nullptr};
     b.build();
@@ -530,13 +536,13 @@ size_t forward_workspace_bytes(const dsb_ctx* ctx, int64_t chunk, int precision)
 void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, const float* means, const float* stds,
                  const float* lens, const float* signals, float* probs, int32_t* pred, cudaStream_t stream) {
   if (!ctx->have_model) fail(DSB_ERR_STATE, "dsb_forward called before dsb_load_weights");
-  if (precision != DSB_PREC_FP32 && precision != DSB_PREC_BF16) fail(DSB_ERR_INVALID, "unknown precision %d", precision);
+  if (precision != DSB_PREC_FP32 && precision != DSB_PREC_BF16 && precision != DSB_PREC_FP16) fail(DSB_ERR_INVALID, "unknown precision %d", precision);
   if (n < 0) fail(DSB_ERR_INVALID, "negative sample count");
   if (n == 0) return;
   if (!signals || !probs || !pred || (ctx->model.has_rnn() && (!means || !stds || !lens || (ctx->model.has_base() && !kmer))))
     fail(DSB_ERR_INVALID, "null input/output pointer");
-  if (precision == DSB_PREC_BF16 && ctx->cc_major != 10)
-    fail(DSB_ERR_ARCH, "the bf16 tensor-core path needs an sm_100 device (found sm_%d%d); there is no fallback", ctx->cc_major, ctx->cc_minor);
+  if (precision != DSB_PREC_FP32 && ctx->cc_major != 10)
+    fail(DSB_ERR_ARCH, "the 16-bit tensor-core path needs an sm_100 device (found sm_%d%d); there is no fallback", ctx->cc_major, ctx->cc_minor);
   DSB_CUDA(cudaSetDevice(ctx->device));
   const int64_t want = std::min<int64_t>(ctx->max_chunk, (n + 127) / 128 * 128);
   auto& slot = ctx->plan[precision];
@@ -550,6 +556,7 @@ void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, co
     DSB_CUDA(cudaEventCreateWithFlags(&np->ev_join[0], cudaEventDisableTiming));
     DSB_CUDA(cudaEventCreateWithFlags(&np->ev_join[1], cudaEventDisableTiming));
     if (precision == DSB_PREC_FP32) build_plan<float>(ctx, *np, want, stream);
+    else if (precision == DSB_PREC_FP16) build_plan<__half>(ctx, *np, want, stream);
     else build_plan<__nv_bfloat16>(ctx, *np, want, stream);
     slot = std::move(np);
   }
@@ -563,6 +570,8 @@ void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, co
     const float* ln = lens ? lens + off * KL : nullptr;
     if (precision == DSB_PREC_FP32)
       run_chunk<float>(ctx, plan, m, k, mu, sd, ln, signals + off * S, probs + off * 2, pred + off, stream);
+    else if (precision == DSB_PREC_FP16)
+      run_chunk<__half>(ctx, plan, m, k, mu, sd, ln, signals + off * S, probs + off * 2, pred + off, stream);
     else
       run_chunk<__nv_bfloat16>(ctx, plan, m, k, mu, sd, ln, signals + off * S, probs + off * 2, pred + off, stream);
   }

@@ -10,6 +10,8 @@
 // Accumulators are double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  A-operand "segments" give k-tap convs (row-shifted TMA boxes; out-of-range rows are
 // zero-filled by TMA, sample edges read the zero halo rows) and [x_t | h_{t-1}] for the LSTM.
+#include <cuda_fp16.h>
+
 #include "gemm_tc.cuh"
 
 namespace dsb {
@@ -92,12 +94,21 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
+template <bool F16> __device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if constexpr (F16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+}
+template <bool F16> __device__ __forceinline__ float2 unpack16(uint32_t w) {
+  if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  else return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 
-template <int BK, int EPI>
+template <int BK, int EPI, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const int m_tiles, const uint32_t tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
@@ -157,9 +168,10 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      // kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A/B,
+      // kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A/B format at bits 7-9 / 10-12, K-major A/B,
       // N>>3 at bits 17-22, M>>4 at bits 24-28.
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM_TC >> 4) << 24);
+      const uint32_t fmt = F16 ? 0u : 1u;   // F16F32Format: 0 = F16, 1 = BF16
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM_TC >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -216,15 +228,16 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
           if (!row_ok) continue;
           const bool first = col < e.split;
           if (e.res != nullptr && first) {
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.res) + (size_t)row * e.res_ld + e.res_c0 + col);
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.res) + (size_t)row * e.res_ld + e.res_c0 + col);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const uint4 rv = __ldg(rp + h);
               const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                v[8 * h + 2 * i] += __uint_as_float(w[i] << 16);
-                v[8 * h + 2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+                const float2 f = unpack16<F16>(w[i]);
+                v[8 * h + 2 * i] += f.x;
+                v[8 * h + 2 * i + 1] += f.y;
               }
             }
           }
@@ -236,11 +249,11 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = 0.f;
           }
-          __nv_bfloat16* dst = first ? reinterpret_cast<__nv_bfloat16*>(e.d0) + (size_t)row * e.ld0 + e.c0 + col
-                                     : reinterpret_cast<__nv_bfloat16*>(e.d1) + (size_t)row * e.ld1 + e.c1 + col - e.split;
+          uint16_t* dst = first ? reinterpret_cast<uint16_t*>(e.d0) + (size_t)row * e.ld0 + e.c0 + col
+                                : reinterpret_cast<uint16_t*>(e.d1) + (size_t)row * e.ld1 + e.c1 + col - e.split;
           uint4* dp = reinterpret_cast<uint4*>(dst);
-          dp[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-          dp[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+          dp[0] = make_uint4(pack16<F16>(v[0], v[1]), pack16<F16>(v[2], v[3]), pack16<F16>(v[4], v[5]), pack16<F16>(v[6], v[7]));
+          dp[1] = make_uint4(pack16<F16>(v[8], v[9]), pack16<F16>(v[10], v[11]), pack16<F16>(v[12], v[13]), pack16<F16>(v[14], v[15]));
         }
       } else {
         // LSTM: columns 4*u+g.  64 columns (16 hidden units) per iteration.
@@ -269,9 +282,9 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
             }
             *reinterpret_cast<float4*>(cp + 4 * i) = make_float4(cn[0], cn[1], cn[2], cn[3]);
           }
-          uint4* hp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.h_out) + (size_t)row * HID + u0);
-          hp[0] = make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]), pack_bf16(hn[6], hn[7]));
-          hp[1] = make_uint4(pack_bf16(hn[8], hn[9]), pack_bf16(hn[10], hn[11]), pack_bf16(hn[12], hn[13]), pack_bf16(hn[14], hn[15]));
+          uint4* hp = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.h_out) + (size_t)row * HID + u0);
+          hp[0] = make_uint4(pack16<F16>(hn[0], hn[1]), pack16<F16>(hn[2], hn[3]), pack16<F16>(hn[4], hn[5]), pack16<F16>(hn[6], hn[7]));
+          hp[1] = make_uint4(pack16<F16>(hn[8], hn[9]), pack16<F16>(hn[10], hn[11]), pack16<F16>(hn[12], hn[13]), pack16<F16>(hn[14], hn[15]));
         }
       }
       tc_fence_before();
@@ -305,9 +318,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BK, int EPI>
+template <int BK, int EPI, bool F16>
 void launch_one(const TcLaunch& L, int m_tiles, int grid, uint32_t tmem_cols, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<BK, EPI>;
+  auto kern = gemm_tc_kernel<BK, EPI, F16>;
   static bool configured[64] = {false};
   int dev = 0;
   DSB_CUDA(cudaGetDevice(&dev));
@@ -321,8 +334,8 @@ void launch_one(const TcLaunch& L, int m_tiles, int grid, uint32_t tmem_cols, cu
 
 }  // namespace
 
-void encode_map_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
-                     int box_rows, int box_cols) {
+void encode_map_16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                   int box_rows, int box_cols, bool fp16) {
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
@@ -331,7 +344,7 @@ void encode_map_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t c
                               : (box_cols * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
   if (sw == CU_TENSOR_MAP_SWIZZLE_NONE) fail(DSB_ERR_INVALID, "tensor map box must span 64 or 128 bytes");
   if (((uintptr_t)base & 15) || ((ld * 2) & 15)) fail(DSB_ERR_INVALID, "tensor map base/stride must be 16-byte aligned");
-  CUresult r = get_encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = get_encode_fn()(out, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fail(DSB_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld box=%dx%d)",
@@ -366,12 +379,15 @@ void launch_gemm_tc(const TcLaunch& L, int M, int sm_count, cudaStream_t s) {
   while (cols < (uint32_t)(2 * L.p.BN)) cols <<= 1;
   TcLaunch Lr = L;
   Lr.p.epi.M = M;
-  if (L.BK == 64) {
-    if (L.epi_kind == EPI_CONV) launch_one<64, EPI_CONV>(Lr, m_tiles, grid, cols, s);
-    else launch_one<64, EPI_LSTM>(Lr, m_tiles, grid, cols, s);
-  } else {
-    if (L.epi_kind == EPI_CONV) launch_one<32, EPI_CONV>(Lr, m_tiles, grid, cols, s);
-    else fail(DSB_ERR_INVALID, "LSTM epilogue needs BK=64");
+  const int key = (L.BK == 64 ? 0 : 4) | (L.epi_kind == EPI_CONV ? 0 : 2) | (L.fp16 ? 1 : 0);
+  switch (key) {
+    case 0: launch_one<64, EPI_CONV, false>(Lr, m_tiles, grid, cols, s); break;
+    case 1: launch_one<64, EPI_CONV, true>(Lr, m_tiles, grid, cols, s); break;
+    case 2: launch_one<64, EPI_LSTM, false>(Lr, m_tiles, grid, cols, s); break;
+    case 3: launch_one<64, EPI_LSTM, true>(Lr, m_tiles, grid, cols, s); break;
+    case 4: launch_one<32, EPI_CONV, false>(Lr, m_tiles, grid, cols, s); break;
+    case 5: launch_one<32, EPI_CONV, true>(Lr, m_tiles, grid, cols, s); break;
+    default: fail(DSB_ERR_INVALID, "LSTM epilogue needs BK=64");
   }
 }
 

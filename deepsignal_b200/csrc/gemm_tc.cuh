@@ -29,14 +29,15 @@ struct TcLaunch {         // everything needed to launch one prebuilt GEMM
   GemmTCParams p;
   int BK = 64;            // 64 -> SWIZZLE_128B tiles, 32 -> SWIZZLE_64B tiles
   int epi_kind = EPI_CONV;
+  bool fp16 = false;       // operand / output element type: false = bf16, true = fp16 (both kind::f16)
   size_t smem = 0;
   double flops_per_row = 0;
 };
 
-// Encode a 2-D bf16 row-major [rows][cols] (leading dimension ld elements) tensor map with a
+// Encode a 2-D bf16/fp16 row-major [rows][cols] (leading dimension ld elements) tensor map with a
 // [box_rows][box_cols] box; box_cols*2 bytes must equal the swizzle span (128 or 64).
-void encode_map_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
-                     int box_rows, int box_cols);
+void encode_map_16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                   int box_rows, int box_cols, bool fp16);
 void finalize_tc_launch(TcLaunch& L);                       // picks stages / smem
 void launch_gemm_tc(const TcLaunch& L, int M, int sm_count, cudaStream_t s);
 

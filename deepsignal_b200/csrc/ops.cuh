@@ -5,6 +5,8 @@
 // where the A "segments" cover 1x1 convs (one segment), k-tap convs (one segment per tap, drow = tap - pad,
 // reading the zero halo rows of the padded row layout at sample edges) and LSTM steps (x_t | h_{t-1}).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace dsb {
@@ -45,7 +47,9 @@ struct GemmF32Params {
 template <class T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 template <class T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 

@@ -142,7 +142,7 @@ def random_checkpoint(seed: int = 17, variant: str = "stress", **model_kw):
         elif leaf == "kernel":
             gain = 1.0
             if variant == "stress" and name == "dense_1/kernel":
-                gain = 0.1
+                gain = 0.05
             ck[name] = _glorot(rng, shape, shape[0], shape[1], gain)
         elif leaf == "bias":
             ck[name] = (rng.normal(0, 0.1, size=shape).astype(np.float32) if variant == "stress"

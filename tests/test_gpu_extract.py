@@ -94,7 +94,7 @@ def test_zscore_no_reference_and_motif_variants(engine):
     want = _oracle(rb, ["CG"], chrom2len=None, method="zscore")
     _compare(got, want, exact_floats=False)
     assert np.all(got["pos_in_strand"] == -1)
-    for motif, loc in (("CHG", 0), ("CCWGG", 1), ("CHH,CG", 0), ("NCG", 1)):
+    for motif, loc in (("CHG", 0), ("CCWGG", 1), ("CHH,CHG", 0), ("NCG", 1)):
         ms = get_motif_seqs(motif)
         got = engine.extract(rb, ms, mod_loc=loc)
         want = _oracle(rb, ms, mod_loc=loc, chrom2len=None)
