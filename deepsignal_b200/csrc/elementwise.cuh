@@ -99,25 +99,44 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
   __syncthreads();
   T* out = reinterpret_cast<T*>(p.out) + (size_t)s * p.Lp2 * 64;
   const int c = threadIdx.x & 63;
+  const int strip = threadIdx.x >> 6, nstrip = blockDim.x >> 6;
   float w[7];
 #pragma unroll
   for (int t = 0; t < 7; ++t) w[t] = ws[c * 7 + t];
   const float b = bs[c];
-  for (int pos = threadIdx.x >> 6; pos < p.Lp2; pos += blockDim.x >> 6) {
-    float best = 0.f;   // ReLU output >= 0 and every pool window holds >= 1 valid cell
-    if (pos < p.L2) {
+  // each thread walks a strip of pooled positions; conv positions advance by one (signal index by two), so the
+  // 7-sample window slides in registers and conv(2p+2) is reused as conv(2(p+1)).
+  const int per = (p.Lp2 + nstrip - 1) / nstrip;
+  const int p0 = strip * per, p1 = min(p.Lp2, p0 + per);
+  if (p0 >= p1) return;
+  int q = 2 * p0 - p.pool_pl;                    // first conv position needed
+  int x0 = 2 * q - p.conv_pl + 8;                // window start in xs (x0 >= 0 is guaranteed by the 8-sample pad for q >= -3)
+  float win[7];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int q = 2 * pos - p.pool_pl + k;      // conv1 position
-        if (q < 0 || q >= p.L1) continue;
-        const int x0 = 2 * q - p.conv_pl + 8;       // index into xs
-        float a = b;
+  for (int t = 0; t < 7; ++t) win[t] = (x0 + t >= 0 && x0 + t < p.S + 16) ? xs[x0 + t] : 0.f;
+  auto conv_here = [&]() {
+    float a = b;
 #pragma unroll
-        for (int t = 0; t < 7; ++t) a = fmaf(w[t], xs[x0 + t], a);
-        best = fmaxf(best, a);
-      }
-    }
+    for (int t = 0; t < 7; ++t) a = fmaf(w[t], win[t], a);
+    return (q >= 0 && q < p.L1) ? fmaxf(a, 0.f) : 0.f;     // ReLU; invalid cells contribute 0 (<= every valid value)
+  };
+  auto slide = [&]() {
+    ++q;
+    x0 += 2;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) win[t] = win[t + 2];
+    win[5] = (x0 + 5 < p.S + 16) ? xs[x0 + 5] : 0.f;
+    win[6] = (x0 + 6 < p.S + 16) ? xs[x0 + 6] : 0.f;
+  };
+  float c0 = conv_here();
+  for (int pos = p0; pos < p1; ++pos) {
+    slide();
+    const float c1 = conv_here();
+    slide();
+    const float c2 = conv_here();
+    const float best = (pos < p.L2) ? fmaxf(c0, fmaxf(c1, c2)) : 0.f;
     out[(size_t)pos * 64 + c] = from_f32<T>(best);
+    c0 = c2;
   }
 }
 
@@ -179,16 +198,14 @@ __global__ void lstm_feat_kernel(const int32_t* __restrict__ kmer, const float* 
   if (idx >= n * klen) return;
   const int64_t s = idx / klen;
   const int pos = (int)(idx % klen);
-  T* f = F + ((int64_t)pos * cap + s) * FW;
   const int code = use_base ? kmer[idx] : -1;
-  for (int j = 0; j < FW; ++j) {
-    float v = 0.f;
-    if (j < 5) v = (j == code) ? 1.f : 0.f;
-    else if (j == 5) v = means[idx];
-    else if (j == 6) v = stds[idx];
-    else if (j == 7) v = lens[idx];
-    f[j] = from_f32<T>(v);
-  }
+  Vec8<T> v;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) v.v[j] = (j == code) ? 1.f : 0.f;
+  v.v[5] = means[idx];
+  v.v[6] = stds[idx];
+  v.v[7] = lens[idx];
+  v.store(F + ((int64_t)pos * cap + s) * FW);     // columns 8..FW-1 stay zero (workspace is zeroed at plan build)
 }
 
 // ---- head: logits = h_fw·Wr[0:256] + h_bw·Wr[256:512] + sum_{p,c} y[s*Lp+p][c]·Wc[p][c] ------------
@@ -204,54 +221,61 @@ struct HeadParams {
 
 template <class T>
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
+  extern __shared__ float hw[];                    // Wc [L*240*2] then Wr [1024]
+  const int ncnn = (p.y != nullptr) ? p.L * CH * 2 : 0;
+  for (int i = threadIdx.x; i < ncnn; i += blockDim.x) hw[i] = p.Wc[i];
+  if (p.hfw != nullptr) for (int i = threadIdx.x; i < 4 * HID; i += blockDim.x) hw[ncnn + i] = p.Wr[i];
+  __syncthreads();
+  const float* wr = hw + ncnn;
   const int lane = threadIdx.x & 31;
-  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (s >= p.n) return;
-  float a0 = 0.f, a1 = 0.f;
-  if (p.y != nullptr) {
-    const T* y = reinterpret_cast<const T*>(p.y) + s * p.Lp * CH;
-    const int nv = p.L * CH / 8;                 // contiguous: rows 0..L-1 of this sample
-    for (int i = lane; i < nv; i += 32) {
-      const Vec8<T> v = Vec8<T>::load(y + i * 8);
-      const float4* w = reinterpret_cast<const float4*>(p.Wc + (size_t)i * 16);
+  const int wpb = blockDim.x >> 5;
+  for (int64_t s = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); s < p.n; s += (int64_t)gridDim.x * wpb) {
+    float a0 = 0.f, a1 = 0.f;
+    if (p.y != nullptr) {
+      const T* y = reinterpret_cast<const T*>(p.y) + s * p.Lp * CH;
+      const int nv = p.L * CH / 8;                 // contiguous: rows 0..L-1 of this sample
+      for (int i = lane; i < nv; i += 32) {
+        const Vec8<T> v = Vec8<T>::load(y + i * 8);
+        const float4* w = reinterpret_cast<const float4*>(hw + (size_t)i * 16);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 ww = __ldg(w + q);
-        a0 = fmaf(v.v[2 * q], ww.x, a0); a1 = fmaf(v.v[2 * q], ww.y, a1);
-        a0 = fmaf(v.v[2 * q + 1], ww.z, a0); a1 = fmaf(v.v[2 * q + 1], ww.w, a1);
+        for (int q = 0; q < 4; ++q) {
+          const float4 ww = w[q];
+          a0 = fmaf(v.v[2 * q], ww.x, a0); a1 = fmaf(v.v[2 * q], ww.y, a1);
+          a0 = fmaf(v.v[2 * q + 1], ww.z, a0); a1 = fmaf(v.v[2 * q + 1], ww.w, a1);
+        }
       }
     }
-  }
-  if (p.hfw != nullptr) {
-    const T* hf = reinterpret_cast<const T*>(p.hfw) + s * HID;
-    const T* hb = reinterpret_cast<const T*>(p.hbw) + s * HID;
-    {
-      const Vec8<T> v = Vec8<T>::load(hf + lane * 8);
+    if (p.hfw != nullptr) {
+      const T* hf = reinterpret_cast<const T*>(p.hfw) + s * HID;
+      const T* hb = reinterpret_cast<const T*>(p.hbw) + s * HID;
+      {
+        const Vec8<T> v = Vec8<T>::load(hf + lane * 8);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float2 ww = __ldg(reinterpret_cast<const float2*>(p.Wr) + lane * 8 + q);
-        a0 = fmaf(v.v[q], ww.x, a0); a1 = fmaf(v.v[q], ww.y, a1);
+        for (int q = 0; q < 8; ++q) {
+          const float2 ww = reinterpret_cast<const float2*>(wr)[lane * 8 + q];
+          a0 = fmaf(v.v[q], ww.x, a0); a1 = fmaf(v.v[q], ww.y, a1);
+        }
+      }
+      {
+        const Vec8<T> v = Vec8<T>::load(hb + lane * 8);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float2 ww = reinterpret_cast<const float2*>(wr)[HID + lane * 8 + q];
+          a0 = fmaf(v.v[q], ww.x, a0); a1 = fmaf(v.v[q], ww.y, a1);
+        }
       }
     }
-    {
-      const Vec8<T> v = Vec8<T>::load(hb + lane * 8);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float2 ww = __ldg(reinterpret_cast<const float2*>(p.Wr) + HID + lane * 8 + q);
-        a0 = fmaf(v.v[q], ww.x, a0); a1 = fmaf(v.v[q], ww.y, a1);
-      }
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
     }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-  }
-  if (lane == 0) {
-    const float p0 = 1.0f / (1.0f + expf(-a0)), p1 = 1.0f / (1.0f + expf(-a1));
-    p.probs[2 * s] = p0;
-    p.probs[2 * s + 1] = p1;
-    p.pred[s] = (p1 > p0) ? 1 : 0;     // argmax, ties -> 0
+    if (lane == 0) {
+      const float p0 = 1.0f / (1.0f + expf(-a0)), p1 = 1.0f / (1.0f + expf(-a1));
+      p.probs[2 * s] = p0;
+      p.probs[2 * s + 1] = p1;
+      p.pred[s] = (p1 > p0) ? 1 : 0;     // argmax, ties -> 0
+    }
   }
 }
 

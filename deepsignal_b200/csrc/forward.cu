@@ -168,10 +168,10 @@ struct Builder {
       if (nmaps == 1) L.maps.a[1] = L.maps.a[0];
       if (kt != W.Ktot) fail(DSB_ERR_STATE, "internal: bf16 GEMM K mismatch %d vs %d", kt, W.Ktot);
       L.p.BN = W.N <= 256 ? W.N : 256;
-      encode_map_16(&L.maps.b, W.w, W.N, W.Ktot, W.Ktot, L.p.BN, BK, std::is_same<T, __half>::value);
       L.p.epi = epi;
       L.flops_per_row = st.flops_per_row;
-      finalize_tc_launch(L);
+      finalize_tc_launch(L);      // may shrink BN so that the weights stay resident in shared memory
+      encode_map_16(&L.maps.b, W.w, W.N, W.Ktot, W.Ktot, L.p.BN, BK, std::is_same<T, __half>::value);
     }
     plan.steps.push_back(st);
   }
@@ -502,7 +502,14 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
         p.probs = probs;
         p.pred = pred;
         p.n = n;
-        head_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, s>>>(p);
+        const size_t hsm = ((p.y ? (size_t)p.L * CH * 2 : 0) + 4 * HID) * sizeof(float);
+        static bool head_cfg[64] = {false};
+        if (!head_cfg[ctx->device & 63]) {
+          DSB_CUDA(cudaFuncSetAttribute(head_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+          head_cfg[ctx->device & 63] = true;
+        }
+        const unsigned hgrid = (unsigned)std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 3);
+        head_kernel<T><<<hgrid, 256, hsm, s>>>(p);
         DSB_CUDA(cudaGetLastError());
         ctx->launches++;
         break;

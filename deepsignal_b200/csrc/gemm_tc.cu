@@ -1,11 +1,11 @@
 // gemm_tc.cu — bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands
 // staged by TMA) with the conv / LSTM epilogues fused.  sm_100a only; this is the DSB_PREC_BF16 path.
 //
-// One persistent CTA per SM, 192 threads:
+// One persistent CTA per SM, 320 threads:
 //   warp 0      TMA producer  (one elected lane): A tile [128 x BK] + B tile [BN x BK] per stage
 //   warp 1      TMEM allocator + MMA issuer (one elected lane): BK/16 tcgen05.mma per stage,
 //               tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 16 columns, bias / residual / ReLU / halo-row zeroing
+//   warps 2..9  epilogue (two warps per TMEM lane quadrant): tcgen05.ld 32 lanes x 16 columns, bias / residual / ReLU / halo-row zeroing
 //               (conv) or the LSTM cell update, bf16 stores
 // Accumulators are double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  A-operand "segments" give k-tap convs (row-shifted TMA boxes; out-of-range rows are
@@ -17,7 +17,7 @@
 namespace dsb {
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int BM_TC = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,24 +115,38 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.BN;
-  const uint32_t a_bytes = BM_TC * BK * 2, b_bytes = (uint32_t)BN * BK * 2, stage_bytes = a_bytes + b_bytes;
+  const uint32_t a_bytes = BM_TC * BK * 2, b_bytes = (uint32_t)BN * BK * 2;
+  const bool resident = p.resident != 0;
+  int total_kb = 0;
+  for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
+  const uint32_t stage_bytes = resident ? a_bytes : a_bytes + b_bytes;
+  const uint32_t bres_base = smem_base;                                   // resident B: total_kb blocks of b_bytes
+  const uint32_t ring_base = smem_base + (resident ? (uint32_t)total_kb * b_bytes : 0u);
   const int stages = p.stages;
-  const uint32_t bar_base = smem_base + stages * stage_bytes;   // 8-byte barriers
+  const uint32_t bar_base = ring_base + stages * stage_bytes;   // 8-byte barriers
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  const uint32_t bres_bar = bar_base + 8u * (2 * stages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 6);
+  float* sbias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));   // [N] floats
   const int n_tiles_n = p.epi.N / BN;
-  const int num_tiles = m_tiles * n_tiles_n;
-  int total_kb = 0;
-  for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
+  // tile walk: streaming mode interleaves (m, n) tiles over all CTAs; resident mode pins a CTA to one n tile
+  const int my_n = resident ? (int)(blockIdx.x % n_tiles_n) : 0;
+  const int t_begin = resident ? (int)(blockIdx.x / n_tiles_n) : (int)blockIdx.x;
+  const int t_step = resident ? (int)(gridDim.x / n_tiles_n) : (int)gridDim.x;
+  const int num_tiles = resident ? m_tiles : m_tiles * n_tiles_n;
+  auto tile_m = [&](int t) { return resident ? t : t / n_tiles_n; };
+  auto tile_n = [&](int t) { return resident ? my_n : t % n_tiles_n; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < p.epi.N; i += TC_THREADS) sbias[i] = p.epi.bias[i];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -148,17 +162,21 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int row0 = (tile / n_tiles_n) * BM_TC, n0 = (tile % n_tiles_n) * BN;
+      if (resident && t_begin < num_tiles) {
+        mbar_expect_tx(bres_bar, (uint32_t)total_kb * b_bytes);
+        for (int kb = 0; kb < total_kb; ++kb) tma_load_2d(bres_base + kb * b_bytes, &maps.b, bres_bar, kb * BK, my_n * BN);
+      }
+      for (int tile = t_begin; tile < num_tiles; tile += t_step) {
+        const int row0 = tile_m(tile) * BM_TC, n0 = tile_n(tile) * BN;
         int kb_global = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const SegTC sg = p.seg[s];
           for (int j = 0; j < sg.nkb; ++j) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), stage_bytes);
-            const uint32_t a_dst = smem_base + stage * stage_bytes;
+            const uint32_t a_dst = ring_base + stage * stage_bytes;
             tma_load_2d(a_dst, &maps.a[sg.map], full_bar(stage), sg.col0 + j * BK, row0 + sg.drow);
-            tma_load_2d(a_dst + a_bytes, &maps.b, full_bar(stage), kb_global * BK, n0);
+            if (!resident) tma_load_2d(a_dst + a_bytes, &maps.b, full_bar(stage), kb_global * BK, n0);
             ++kb_global;
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
@@ -174,16 +192,17 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM_TC >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (resident && t_begin < num_tiles) mbar_wait(bres_bar, 0);
+      for (int tile = t_begin; tile < num_tiles; tile += t_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint32_t a_addr = ring_base + stage * stage_bytes;
           const uint64_t adesc = make_kmajor_desc<BK>(a_addr);
-          const uint64_t bdesc = make_kmajor_desc<BK>(a_addr + a_bytes);
+          const uint64_t bdesc = make_kmajor_desc<BK>(resident ? bres_base + kb * b_bytes : a_addr + a_bytes);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -196,68 +215,76 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
       }
     }
   } else {
-    // ================= epilogue warps =================
+    // ================= epilogue warps (8: two per TMEM lane quadrant, interleaved column groups) =================
     const int q = warp & 3;                   // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;         // which of the two interleaved column-group sets
     const EpiParams& e = p.epi;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int row = (tile / n_tiles_n) * BM_TC + q * 32 + lane;
-      const int n0 = (tile % n_tiles_n) * BN;
+    for (int tile = t_begin; tile < num_tiles; tile += t_step) {
+      const int row = tile_m(tile) * BM_TC + q * 32 + lane;
+      const int n0 = tile_n(tile) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       const bool row_ok = row < e.M;
       if constexpr (EPI == EPI_CONV) {
         const bool halo = e.Lp > 0 && (row % e.Lp) >= e.L;
-        for (int c = 0; c < BN; c += 16) {
-          uint32_t r[16];
+        // 32-column groups; group g belongs to the warp set (g & 1) == half
+        for (int c = half * 32; c < BN; c += 64) {
+          const bool two = c + 32 <= BN;       // BN is a multiple of 16: the last group may hold 16 columns
+          uint32_t r[2][16];
           __syncwarp();
-          tc_ld16(t_row + (uint32_t)c, r);
+          tc_ld16(t_row + (uint32_t)c, r[0]);
+          if (two) tc_ld16(t_row + (uint32_t)(c + 16), r[1]);
           tc_wait_ld();
-          const int col = n0 + c;
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col) + i);
-            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + b.x;
-            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b.y;
-            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b.z;
-            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b.w;
-          }
           if (!row_ok) continue;
-          const bool first = col < e.split;
-          if (e.res != nullptr && first) {
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.res) + (size_t)row * e.res_ld + e.res_c0 + col);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint4 rv = __ldg(rp + h);
-              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+          for (int h2 = 0; h2 < 2; ++h2) {
+            if (h2 == 1 && !two) break;
+            const int col = n0 + c + 16 * h2;
+            float v[16];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack16<F16>(w[i]);
-                v[8 * h + 2 * i] += f.x;
-                v[8 * h + 2 * i + 1] += f.y;
+            for (int i = 0; i < 4; ++i) {
+              const float4 bb = *reinterpret_cast<const float4*>(sbias + col + 4 * i);
+              v[4 * i + 0] = __uint_as_float(r[h2][4 * i + 0]) + bb.x;
+              v[4 * i + 1] = __uint_as_float(r[h2][4 * i + 1]) + bb.y;
+              v[4 * i + 2] = __uint_as_float(r[h2][4 * i + 2]) + bb.z;
+              v[4 * i + 3] = __uint_as_float(r[h2][4 * i + 3]) + bb.w;
+            }
+            const bool first = col < e.split;
+            if (e.res != nullptr && first) {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.res) + (size_t)row * e.res_ld + e.res_c0 + col);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint4 rv = __ldg(rp + h);
+                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = unpack16<F16>(w[i]);
+                  v[8 * h + 2 * i] += f.x;
+                  v[8 * h + 2 * i + 1] += f.y;
+                }
               }
             }
-          }
-          if ((e.relu_mask >> (col >> 4)) & 1u) {
+            if ((e.relu_mask >> (col >> 4)) & 1u) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (halo) {
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (halo) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+              for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+            uint16_t* dst = first ? reinterpret_cast<uint16_t*>(e.d0) + (size_t)row * e.ld0 + e.c0 + col
+                                  : reinterpret_cast<uint16_t*>(e.d1) + (size_t)row * e.ld1 + e.c1 + col - e.split;
+            uint4* dp = reinterpret_cast<uint4*>(dst);
+            dp[0] = make_uint4(pack16<F16>(v[0], v[1]), pack16<F16>(v[2], v[3]), pack16<F16>(v[4], v[5]), pack16<F16>(v[6], v[7]));
+            dp[1] = make_uint4(pack16<F16>(v[8], v[9]), pack16<F16>(v[10], v[11]), pack16<F16>(v[12], v[13]), pack16<F16>(v[14], v[15]));
           }
-          uint16_t* dst = first ? reinterpret_cast<uint16_t*>(e.d0) + (size_t)row * e.ld0 + e.c0 + col
-                                : reinterpret_cast<uint16_t*>(e.d1) + (size_t)row * e.ld1 + e.c1 + col - e.split;
-          uint4* dp = reinterpret_cast<uint4*>(dst);
-          dp[0] = make_uint4(pack16<F16>(v[0], v[1]), pack16<F16>(v[2], v[3]), pack16<F16>(v[4], v[5]), pack16<F16>(v[6], v[7]));
-          dp[1] = make_uint4(pack16<F16>(v[8], v[9]), pack16<F16>(v[10], v[11]), pack16<F16>(v[12], v[13]), pack16<F16>(v[14], v[15]));
         }
       } else {
-        // LSTM: columns 4*u+g.  64 columns (16 hidden units) per iteration.
-        for (int c = 0; c < BN; c += 64) {
+        // LSTM: columns 4*u+g.  64 columns (16 hidden units) per iteration, iterations interleaved over the two warp sets.
+        for (int c = half * 64; c < BN; c += 128) {
           uint32_t r[4][16];
           __syncwarp();
 #pragma unroll
@@ -275,7 +302,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
             float cn[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col + 16 * i + 4 * j));
+              const float4 b = *reinterpret_cast<const float4*>(sbias + col + 16 * i + 4 * j);
               lstm_unit<true>(__uint_as_float(r[i][4 * j + 0]) + b.x, __uint_as_float(r[i][4 * j + 1]) + b.y,
                               __uint_as_float(r[i][4 * j + 2]) + b.z, __uint_as_float(r[i][4 * j + 3]) + b.w,
                               cpv[j], cn[j], hn[4 * i + j]);
@@ -352,29 +379,46 @@ void encode_map_16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
 }
 
 void finalize_tc_launch(TcLaunch& L) {
-  const size_t stage_bytes = (size_t)(BM_TC + L.p.BN) * L.BK * 2;
+  if (L.p.BN % 16 != 0 || L.p.BN < 16 || L.p.BN > 256 || L.p.epi.N % L.p.BN != 0)
+    fail(DSB_ERR_INVALID, "bad GEMM tile: N=%d BN=%d", L.p.epi.N, L.p.BN);
   int total_kb = 0;
   for (int s = 0; s < L.p.nseg; ++s) total_kb += L.p.seg[s].nkb;
+  const size_t a_bytes = (size_t)BM_TC * L.BK * 2;
   const size_t budget = 200 * 1024;
-  int stages = (int)(budget / stage_bytes);
+  // conv weights are small: keep the whole [BN x K] operand in shared memory when it leaves room for >= 4 A stages
+  L.p.resident = 0;
+  if (L.epi_kind == EPI_CONV) {
+    int bn = L.p.BN;
+    while (true) {
+      const size_t bres = (size_t)total_kb * bn * L.BK * 2;
+      if (bres + 4 * a_bytes <= budget && (148 % (L.p.epi.N / bn)) == 0) { L.p.BN = bn; L.p.resident = 1; break; }
+      if (bn % 32 != 0 || L.p.epi.N % (bn / 2) != 0) break;
+      bn /= 2;
+    }
+  }
+  const size_t b_bytes = (size_t)L.p.BN * L.BK * 2;
+  const size_t bres = L.p.resident ? (size_t)total_kb * b_bytes : 0;
+  const size_t stage_bytes = L.p.resident ? a_bytes : a_bytes + b_bytes;
+  int stages = (int)((budget - bres) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   L.p.stages = stages;
-  size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16;
+  size_t smem = 1024 + bres + (size_t)stages * stage_bytes + 8 * (2 * stages + 6) + 16 + (size_t)L.p.epi.N * 4 + 16;
   // 2*BN TMEM columns per CTA: keep co-resident CTAs within the 512-column budget
   const int cols = 2 * L.p.BN;
   if (cols > 256 && smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM
   else if (cols > 128 && smem < 80 * 1024) smem = 80 * 1024;   // at most two
   L.smem = smem;
-  if (L.p.BN % 16 != 0 || L.p.BN < 16 || L.p.BN > 256 || L.p.epi.N % L.p.BN != 0)
-    fail(DSB_ERR_INVALID, "bad GEMM tile: N=%d BN=%d", L.p.epi.N, L.p.BN);
 }
 
 void launch_gemm_tc(const TcLaunch& L, int M, int sm_count, cudaStream_t s) {
   const int m_tiles = (M + BM_TC - 1) / BM_TC;
-  const int num_tiles = m_tiles * (L.p.epi.N / L.p.BN);
-  const int grid = num_tiles < sm_count ? num_tiles : sm_count;
-  if (grid <= 0) return;
+  const int ntn = L.p.epi.N / L.p.BN;
+  const int num_tiles = m_tiles * ntn;
+  int grid = num_tiles < sm_count ? num_tiles : sm_count;
+  if (L.p.resident) grid = (grid / ntn) * ntn;
+  if (grid <= 0) grid = L.p.resident ? ntn : 1;
+  if (m_tiles <= 0) return;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * L.p.BN)) cols <<= 1;
   TcLaunch Lr = L;

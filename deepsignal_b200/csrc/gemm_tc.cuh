@@ -21,6 +21,7 @@ struct GemmTCParams {
   SegTC seg[MAX_SEG];
   int BN = 0;             // N tile (multiple of 16, <= 256, divides epi.N)
   int stages = 0;
+  int resident = 0;       // 1: the CTA's whole B tile [BN x K] is loaded once and stays in smem (conv weights)
   EpiParams epi;
 };
 
