@@ -13,10 +13,11 @@
 
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
+#include "incept_tc.cuh"
 
 namespace dsb {
 
-enum StepKind { ST_GEMM, ST_STEM, ST_POOL1, ST_POOL2, ST_FEAT, ST_HEAD, ST_ZERO };
+enum StepKind { ST_GEMM, ST_STEM, ST_POOL1, ST_POOL2, ST_FEAT, ST_HEAD, ST_ZERO, ST_INCEPT_A, ST_INCEPT_B };
 
 struct SegHost { const void* a; int ld; int cols; int col0; int drow; int K; int map_rows_per_sample; };
 
@@ -27,6 +28,8 @@ struct Step {
   // GEMM
   GemmF32Params f32;
   TcLaunch tc;
+  InceptALaunch ia;
+  InceptBLaunch ib;
   int epi_kind = EPI_CONV;
   int kclass = KC_GEMM;
   double flops_per_row = 0;
@@ -250,32 +253,77 @@ struct Builder {
         DevGemm<T> Wb4 = upload_gemm<T>(wa, fb.b4, tap_parts(5, 32, 32), up_stream);
         DevGemm<T> Wb5b = upload_gemm<T>(wa, fb.b5b, tap_parts(3, 32, 32), up_stream);
         DevGemm<T> Wb5c = upload_gemm<T>(wa, fb.b5c, kparts({{0, 64}}, 64), up_stream);
+        bool fused = false;
+        if constexpr (TC) {
+          const char* ev = getenv("DSB_FUSED");       // DSB_FUSED=0 keeps the seven separate launches (debug / A-B tests)
+          fused = !(ev && ev[0] == '0');
+        }
+        if (fused) {
+          if constexpr (TC) {
+            const bool f16 = std::is_same<T, __half>::value;
+            // concatenated biases in accumulator-column order
+            float* biasA = reinterpret_cast<float*>(wa.take(240 * sizeof(float)));
+            float* biasB = reinterpret_cast<float*>(wa.take(208 * sizeof(float)));
+            Step sa, sb;
+            sa.kind = ST_INCEPT_A; sa.stream = 0; sa.rows_per_sample = Lp; sa.kclass = KC_GEMM;
+            sb.kind = ST_INCEPT_B; sb.stream = 0; sb.rows_per_sample = Lp; sb.kclass = KC_GEMM;
+            sa.flops_per_row = 2.0 * (double)cin * 240.0 * (double)L / (double)Lp;
+            sb.flops_per_row = 2.0 * (96.0 * 48 + 160.0 * 48 + 96.0 * 64 + 64.0 * 48) * (double)L / (double)Lp;
+            if (place) {
+              std::vector<float> ha(240), hb(208);
+              for (int k = 0; k < 192; ++k) ha[k] = fb.p1.bias[k];
+              for (int k = 0; k < 48; ++k) ha[192 + k] = fb.b1.bias[k];
+              for (int k = 0; k < 48; ++k) { hb[k] = fb.b3.bias[k]; hb[48 + k] = fb.b4.bias[k]; hb[160 + k] = fb.b5c.bias[k]; }
+              for (int k = 0; k < 64; ++k) hb[96 + k] = fb.b5b.bias[k];
+              DSB_CUDA(cudaMemcpyAsync(biasA, ha.data(), 240 * sizeof(float), cudaMemcpyHostToDevice, up_stream));
+              DSB_CUDA(cudaMemcpyAsync(biasB, hb.data(), 208 * sizeof(float), cudaMemcpyHostToDevice, up_stream));
+              DSB_CUDA(cudaStreamSynchronize(up_stream));
+              InceptALaunch& A = sa.ia;
+              A.fp16 = f16;
+              encode_map_16(&A.maps.x, X, rows_cap, cin, xld, 128, 64, f16);
+              encode_map_16(&A.maps.wp1, Wp1.w, 192, Wp1.Ktot, Wp1.Ktot, 192, 64, f16);
+              encode_map_16(&A.maps.wb1, Wb1.w, 48, Wb1.Ktot, Wb1.Ktot, 48, 64, f16);
+              A.p.Lp = Lp; A.p.L = L; A.p.Y = Y; A.p.ldY = CH; A.p.T = Tb; A.p.ldT = 144; A.p.bias = biasA;
+              InceptBLaunch& B = sb.ib;
+              B.fp16 = f16;
+              encode_map_16(&B.maps.t, Tb, rows_cap, 144, 144, 128, 32, f16);
+              encode_map_16(&B.maps.w3, Wb3.w, 48, Wb3.Ktot, Wb3.Ktot, 48, 32, f16);
+              encode_map_16(&B.maps.w4, Wb4.w, 48, Wb4.Ktot, Wb4.Ktot, 48, 32, f16);
+              encode_map_16(&B.maps.w5b, Wb5b.w, 64, Wb5b.Ktot, Wb5b.Ktot, 64, 32, f16);
+              encode_map_16(&B.maps.w5c, Wb5c.w, 48, Wb5c.Ktot, Wb5c.Ktot, 48, 32, f16);
+              B.p.Lp = Lp; B.p.L = L; B.p.T = Tb; B.p.ldT = 144; B.p.Y = Y; B.p.ldY = CH; B.p.bias = biasB;
+            }
+            plan.steps.push_back(sa);
+            plan.steps.push_back(sb);
+          }
+        } else {
         {   // branch-1 max pool (1x3, stride 1)
-          Step st;
-          st.kind = ST_POOL1;
-          st.stream = 0;
-          st.rows_per_sample = Lp;
-          st.src = X; st.dst = XP; st.C = xld;
-          plan.steps.push_back(st);
-        }
-        gemm(0, Lp, rows_cap, {SegHost{XP, xld, cin, 0, 0, cin, Lp}}, Wb1, 64, conv_epi(Y, CH, 0, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, cin);
-        {   // fused 1x1s: b2 -> Y[:,48:96] ; b3a|b4a|b5a|stem -> T[:,0:144] (stem without ReLU)
-          EpiParams e = conv_epi(Y, CH, 48, 0x1ffu /* cols 0..143 */, Lp, L);
-          e.split = 48;
-          e.d1 = Tb; e.ld1 = 144; e.c1 = 0;
-          gemm(0, Lp, rows_cap, {SegHost{X, xld, cin, 0, 0, cin, Lp}}, Wp1, 64, e, EPI_CONV, KC_GEMM, L, cin);
-        }
-        gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 0, -1, 32, Lp}, SegHost{Tb, 144, 144, 0, 0, 32, Lp}, SegHost{Tb, 144, 144, 0, 1, 32, Lp}},
-             Wb3, 32, conv_epi(Y, CH, 96, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 96);
-        gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 32, -2, 32, Lp}, SegHost{Tb, 144, 144, 32, -1, 32, Lp}, SegHost{Tb, 144, 144, 32, 0, 32, Lp},
-                               SegHost{Tb, 144, 144, 32, 1, 32, Lp}, SegHost{Tb, 144, 144, 32, 2, 32, Lp}},
-             Wb4, 32, conv_epi(Y, CH, 144, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 160);
-        gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 64, -1, 32, Lp}, SegHost{Tb, 144, 144, 64, 0, 32, Lp}, SegHost{Tb, 144, 144, 64, 1, 32, Lp}},
-             Wb5b, 32, conv_epi(Ub, 64, 0, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 96);
-        {
-          EpiParams e = conv_epi(Y, CH, 192, 0xffffffffu, Lp, L);
-          e.res = Tb; e.res_ld = 144; e.res_c0 = 96;
-          gemm(0, Lp, rows_cap, {SegHost{Ub, 64, 64, 0, 0, 64, Lp}}, Wb5c, 64, e, EPI_CONV, KC_GEMM, L, 64);
+            Step st;
+            st.kind = ST_POOL1;
+            st.stream = 0;
+            st.rows_per_sample = Lp;
+            st.src = X; st.dst = XP; st.C = xld;
+            plan.steps.push_back(st);
+          }
+          gemm(0, Lp, rows_cap, {SegHost{XP, xld, cin, 0, 0, cin, Lp}}, Wb1, 64, conv_epi(Y, CH, 0, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, cin);
+          {   // fused 1x1s: b2 -> Y[:,48:96] ; b3a|b4a|b5a|stem -> T[:,0:144] (stem without ReLU)
+            EpiParams e = conv_epi(Y, CH, 48, 0x1ffu /* cols 0..143 */, Lp, L);
+            e.split = 48;
+            e.d1 = Tb; e.ld1 = 144; e.c1 = 0;
+            gemm(0, Lp, rows_cap, {SegHost{X, xld, cin, 0, 0, cin, Lp}}, Wp1, 64, e, EPI_CONV, KC_GEMM, L, cin);
+          }
+          gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 0, -1, 32, Lp}, SegHost{Tb, 144, 144, 0, 0, 32, Lp}, SegHost{Tb, 144, 144, 0, 1, 32, Lp}},
+               Wb3, 32, conv_epi(Y, CH, 96, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 96);
+          gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 32, -2, 32, Lp}, SegHost{Tb, 144, 144, 32, -1, 32, Lp}, SegHost{Tb, 144, 144, 32, 0, 32, Lp},
+                                 SegHost{Tb, 144, 144, 32, 1, 32, Lp}, SegHost{Tb, 144, 144, 32, 2, 32, Lp}},
+               Wb4, 32, conv_epi(Y, CH, 144, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 160);
+          gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 64, -1, 32, Lp}, SegHost{Tb, 144, 144, 64, 0, 32, Lp}, SegHost{Tb, 144, 144, 64, 1, 32, Lp}},
+               Wb5b, 32, conv_epi(Ub, 64, 0, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 96);
+          {
+            EpiParams e = conv_epi(Y, CH, 192, 0xffffffffu, Lp, L);
+            e.res = Tb; e.res_ld = 144; e.res_c0 = 96;
+            gemm(0, Lp, rows_cap, {SegHost{Ub, 64, 64, 0, 0, 64, Lp}}, Wb5c, 64, e, EPI_CONV, KC_GEMM, L, 64);
+          }
         }
         X = Y;
         xld = CH;
@@ -448,6 +496,22 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
           launch_gemm_tc(st.tc, (int)M, ctx->sm_count, s);
         }
         ctx->launches++;
+        break;
+      }
+      case ST_INCEPT_A: {
+        if constexpr (!std::is_same<T, float>::value) {
+          Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
+          launch_incept_a(st.ia, (int)M, ctx->sm_count, s);
+          ctx->launches++;
+        }
+        break;
+      }
+      case ST_INCEPT_B: {
+        if constexpr (!std::is_same<T, float>::value) {
+          Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
+          launch_incept_b(st.ib, (int)M, ctx->sm_count, s);
+          ctx->launches++;
+        }
         break;
       }
       case ST_STEM: {

@@ -1,0 +1,542 @@
+// incept_tc.cu — the two fused inception-block kernels (see incept_tc.cuh).  Both are persistent,
+// warp-specialised tcgen05 kernels with every conv weight of their half of the block resident in shared
+// memory, a TMA-fed ring of activation tiles, and double-buffered accumulators in TMEM.
+#include "incept_tc.cuh"
+#include "tc_common.cuh"
+
+namespace dsb {
+namespace {
+
+using namespace tc;
+
+template <bool F16> __device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if constexpr (F16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+}
+template <bool F16> __device__ __forceinline__ float2 unpack16(uint32_t w) {
+  if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  else return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <bool F16> __device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) {
+  if constexpr (F16) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+}
+__device__ __forceinline__ uint32_t idesc_f16(bool f16, int n) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ============================================================================================
+// Kernel A
+// ============================================================================================
+constexpr int A_THREADS = 448;       // warp 0 TMA, warp 1 MMA, warps 2-5 pool, warps 6-13 epilogue
+constexpr int A_SLOTS = 6;
+constexpr uint32_t A_SLOT_BYTES = 128 * 64 * 2;        // one [128 x 64] SWIZZLE_128B tile
+constexpr uint32_t A_WP1_BLK = 192 * 64 * 2;           // 24576
+constexpr uint32_t A_WB1_BLK = 48 * 64 * 2;            // 6144
+constexpr int A_NKB = 4;
+constexpr uint32_t A_ACC_STRIDE = 256;                 // TMEM columns per accumulator stage (240 used)
+
+struct ASmem {
+  static constexpr uint32_t wp1 = 0;
+  static constexpr uint32_t wb1 = wp1 + A_NKB * A_WP1_BLK;
+  static constexpr uint32_t ring = wb1 + A_NKB * A_WB1_BLK;
+  static constexpr uint32_t bars = ring + A_SLOTS * A_SLOT_BYTES;
+  // barriers: full_x[S] p1_done[S] full_xp[S] empty[S] wbar tfull[2] tempty[2]
+  static constexpr uint32_t nbars = 4 * A_SLOTS + 5;
+  static constexpr uint32_t tmem_slot = (bars + 8 * nbars + 15u) & ~15u;
+  static constexpr uint32_t bias = tmem_slot + 16;
+  static constexpr uint32_t total = bias + 240 * 4;
+};
+
+template <bool F16>
+__global__ void __launch_bounds__(A_THREADS, 1)
+incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p, const int num_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto full_x = [&](int s) { return base + ASmem::bars + 8u * s; };
+  auto p1_done = [&](int s) { return base + ASmem::bars + 8u * (A_SLOTS + s); };
+  auto full_xp = [&](int s) { return base + ASmem::bars + 8u * (2 * A_SLOTS + s); };
+  auto empty = [&](int s) { return base + ASmem::bars + 8u * (3 * A_SLOTS + s); };
+  const uint32_t wbar = base + ASmem::bars + 8u * (4 * A_SLOTS);
+  auto tfull = [&](int a) { return base + ASmem::bars + 8u * (4 * A_SLOTS + 1 + a); };
+  auto tempty = [&](int a) { return base + ASmem::bars + 8u * (4 * A_SLOTS + 3 + a); };
+  const uint32_t tmem_slot = base + ASmem::tmem_slot;
+  float* sbias = reinterpret_cast<float*>(smem_raw + (base + ASmem::bias - smem_u32(smem_raw)));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < A_SLOTS; ++s) { mbar_init(full_x(s), 1); mbar_init(p1_done(s), 1); mbar_init(full_xp(s), 4); mbar_init(empty(s), 1); }
+    mbar_init(wbar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 240; i += A_THREADS) sbias[i] = p.bias[i];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0 && (int)blockIdx.x < num_tiles) {
+      mbar_expect_tx(wbar, A_NKB * (A_WP1_BLK + A_WB1_BLK));
+      for (int j = 0; j < A_NKB; ++j) {
+        tma_load_2d(base + ASmem::wp1 + j * A_WP1_BLK, &maps.wp1, wbar, j * 64, 0);
+        tma_load_2d(base + ASmem::wb1 + j * A_WB1_BLK, &maps.wb1, wbar, j * 64, 0);
+      }
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * INCEPT_A_TILE_ROWS - 1;
+        for (int j = 0; j < A_NKB; ++j) {
+          mbar_wait(empty(slot), phase ^ 1u);
+          mbar_expect_tx(full_x(slot), A_SLOT_BYTES);
+          tma_load_2d(base + ASmem::ring + slot * A_SLOT_BYTES, &maps.x, full_x(slot), j * 64, row0);
+          if (++slot == A_SLOTS) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0 && (int)blockIdx.x < num_tiles) {
+      const uint32_t id_p1 = idesc_f16(F16, 192), id_b1 = idesc_f16(F16, 48);
+      mbar_wait(wbar, 0);
+      int slot = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_p1 = tmem_base + acc * A_ACC_STRIDE, d_b1 = d_p1 + 192;
+        int s = slot;
+        uint32_t ph = phase;
+        for (int j = 0; j < A_NKB; ++j) {               // p1: x tile straight from TMA
+          mbar_wait(full_x(s), ph);
+          tc_fence_after();
+          const uint64_t ad = make_kmajor_desc<64>(base + ASmem::ring + s * A_SLOT_BYTES);
+          const uint64_t bd = make_kmajor_desc<64>(base + ASmem::wp1 + j * A_WP1_BLK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(d_p1, ad + 2 * k, bd + 2 * k, id_p1, (j | k) != 0 ? 1u : 0u);
+          tc_commit(p1_done(s));
+          if (++s == A_SLOTS) { s = 0; ph ^= 1u; }
+        }
+        s = slot;
+        ph = phase;
+        for (int j = 0; j < A_NKB; ++j) {               // b1: the same slot after the pool warps rewrote it
+          mbar_wait(full_xp(s), ph);
+          tc_fence_after();
+          const uint64_t ad = make_kmajor_desc<64>(base + ASmem::ring + s * A_SLOT_BYTES);
+          const uint64_t bd = make_kmajor_desc<64>(base + ASmem::wb1 + j * A_WB1_BLK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(d_b1, ad + 2 * k, bd + 2 * k, id_b1, (j | k) != 0 ? 1u : 0u);
+          tc_commit(empty(s));
+          if (++s == A_SLOTS) { s = 0; ph ^= 1u; }
+        }
+        slot = s;
+        phase = ph;
+        tc_commit(tfull(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp < 6) {
+    // ---------------- pool warps: maxpool 1x3 over rows, in place ----------------
+    const int r = threadIdx.x - 64;                      // tile row 0..127
+    const uint32_t sw = (uint32_t)(r & 7);
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int j = 0; j < A_NKB; ++j) {
+        const uint32_t tb = base + ASmem::ring + slot * A_SLOT_BYTES;
+        mbar_wait(full_x(slot), phase);
+        uint4 out[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          // logical 16-byte chunk c of row rr sits at physical chunk c ^ (rr & 7)  (SWIZZLE_128B)
+          uint4 v = lds128(tb + (uint32_t)r * 128u + (((uint32_t)c ^ sw) << 4));
+          if (r > 0) {
+            const uint4 u = lds128(tb + (uint32_t)(r - 1) * 128u + (((uint32_t)c ^ (uint32_t)((r - 1) & 7)) << 4));
+            v.x = max16x2<F16>(v.x, u.x); v.y = max16x2<F16>(v.y, u.y); v.z = max16x2<F16>(v.z, u.z); v.w = max16x2<F16>(v.w, u.w);
+          }
+          if (r < 127) {
+            const uint4 u = lds128(tb + (uint32_t)(r + 1) * 128u + (((uint32_t)c ^ (uint32_t)((r + 1) & 7)) << 4));
+            v.x = max16x2<F16>(v.x, u.x); v.y = max16x2<F16>(v.y, u.y); v.z = max16x2<F16>(v.z, u.z); v.w = max16x2<F16>(v.w, u.w);
+          }
+          out[c] = v;
+        }
+        mbar_wait(p1_done(slot), phase);                 // the p1 MMAs have finished reading this slot
+        named_bar_sync(1, 128);                          // every pool thread has finished reading its neighbours
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sts128(tb + (uint32_t)r * 128u + (((uint32_t)c ^ sw) << 4), out[c]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_xp(slot));
+        if (++slot == A_SLOTS) { slot = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ---------------- epilogue warps ----------------
+    const int q = warp & 3;
+    const int half = (warp - 6) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int i = q * 32 + lane;                       // tile row
+      const int row = tile * INCEPT_A_TILE_ROWS - 1 + i;
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * A_ACC_STRIDE;
+      const bool row_ok = i >= 1 && i <= INCEPT_A_TILE_ROWS && row < p.M;
+      const bool halo = (row % p.Lp) >= p.L;
+      for (int c = half * 32; c < 240; c += 64) {
+        const bool two = c + 32 <= 240;
+        uint32_t rr[2][16];
+        __syncwarp();
+        tc_ld16(t_row + (uint32_t)c, rr[0]);
+        if (two) tc_ld16(t_row + (uint32_t)(c + 16), rr[1]);
+        tc_wait_ld();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          if (h2 == 1 && !two) break;
+          const int col = c + 16 * h2;
+          float v[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 bb = *reinterpret_cast<const float4*>(sbias + col + 4 * k);
+            v[4 * k + 0] = __uint_as_float(rr[h2][4 * k + 0]) + bb.x;
+            v[4 * k + 1] = __uint_as_float(rr[h2][4 * k + 1]) + bb.y;
+            v[4 * k + 2] = __uint_as_float(rr[h2][4 * k + 2]) + bb.z;
+            v[4 * k + 3] = __uint_as_float(rr[h2][4 * k + 3]) + bb.w;
+          }
+          const bool relu = !(col >= 144 && col < 192);  // the residual stem keeps its sign
+          if (relu) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
+          }
+          if (halo) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = 0.f;
+          }
+          uint16_t* dst;
+          if (col < 48) dst = reinterpret_cast<uint16_t*>(p.Y) + (size_t)row * p.ldY + 48 + col;            // b2
+          else if (col < 192) dst = reinterpret_cast<uint16_t*>(p.T) + (size_t)row * p.ldT + (col - 48);    // b3a|b4a|b5a|stem
+          else dst = reinterpret_cast<uint16_t*>(p.Y) + (size_t)row * p.ldY + (col - 192);                  // b1
+          uint4* dp = reinterpret_cast<uint4*>(dst);
+          dp[0] = make_uint4(pack16<F16>(v[0], v[1]), pack16<F16>(v[2], v[3]), pack16<F16>(v[4], v[5]), pack16<F16>(v[6], v[7]));
+          dp[1] = make_uint4(pack16<F16>(v[8], v[9]), pack16<F16>(v[10], v[11]), pack16<F16>(v[12], v[13]), pack16<F16>(v[14], v[15]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ============================================================================================
+// Kernel B
+// ============================================================================================
+constexpr int B_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int B_SLOTS = 16;
+constexpr uint32_t B_SLOT_BYTES = 128 * 32 * 2;        // one [128 x 32] SWIZZLE_64B tile
+constexpr uint32_t B_W48_BLK = 48 * 32 * 2;            // 3072
+constexpr uint32_t B_W64_BLK = 64 * 32 * 2;            // 4096
+constexpr uint32_t B_ACC_STRIDE = 256;                 // columns: b3 [0,48) b4 [48,96) b5b [96,160) b5c [160,208)
+constexpr int B_LOADS = 11;                            // b5b x3, b3 x3, b4 x5
+
+struct BSmem {
+  static constexpr uint32_t w3 = 0;
+  static constexpr uint32_t w4 = w3 + 3 * B_W48_BLK;
+  static constexpr uint32_t w5b = w4 + 5 * B_W48_BLK;
+  static constexpr uint32_t w5c = w5b + 3 * B_W64_BLK;
+  static constexpr uint32_t u = w5c + 2 * B_W48_BLK;          // 43008: two [128 x 32] blocks
+  static constexpr uint32_t ring = u + 2 * B_SLOT_BYTES;
+  static constexpr uint32_t bars = ring + B_SLOTS * B_SLOT_BYTES;
+  // barriers: full[S] empty[S] wbar b5b_full[2] u_full tfull[2] tempty[2]
+  static constexpr uint32_t nbars = 2 * B_SLOTS + 8;
+  static constexpr uint32_t tmem_slot = (bars + 8 * nbars + 15u) & ~15u;
+  static constexpr uint32_t bias = tmem_slot + 16;
+  static constexpr uint32_t total = bias + 208 * 4;
+};
+
+template <bool F16>
+__global__ void __launch_bounds__(B_THREADS, 1)
+incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p, const int num_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto full = [&](int s) { return base + BSmem::bars + 8u * s; };
+  auto empty = [&](int s) { return base + BSmem::bars + 8u * (B_SLOTS + s); };
+  const uint32_t wbar = base + BSmem::bars + 8u * (2 * B_SLOTS);
+  auto b5b_full = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + a); };
+  const uint32_t u_full = base + BSmem::bars + 8u * (2 * B_SLOTS + 3);
+  auto tfull = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 4 + a); };
+  auto tempty = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 6 + a); };
+  const uint32_t tmem_slot = base + BSmem::tmem_slot;
+  float* sbias = reinterpret_cast<float*>(smem_raw + (base + BSmem::bias - smem_u32(smem_raw)));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < B_SLOTS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(wbar, 1);
+    mbar_init(u_full, 8);
+    for (int a = 0; a < 2; ++a) { mbar_init(b5b_full(a), 1); mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 208; i += B_THREADS) sbias[i] = p.bias[i];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0 && (int)blockIdx.x < num_tiles) {
+      mbar_expect_tx(wbar, 3 * B_W48_BLK + 5 * B_W48_BLK + 3 * B_W64_BLK + 2 * B_W48_BLK);
+      for (int t = 0; t < 3; ++t) tma_load_2d(base + BSmem::w3 + t * B_W48_BLK, &maps.w3, wbar, t * 32, 0);
+      for (int t = 0; t < 5; ++t) tma_load_2d(base + BSmem::w4 + t * B_W48_BLK, &maps.w4, wbar, t * 32, 0);
+      for (int t = 0; t < 3; ++t) tma_load_2d(base + BSmem::w5b + t * B_W64_BLK, &maps.w5b, wbar, t * 32, 0);
+      for (int t = 0; t < 2; ++t) tma_load_2d(base + BSmem::w5c + t * B_W48_BLK, &maps.w5c, wbar, t * 32, 0);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * 128;
+        // order of consumption: b5b taps (T cols 64..95), b3 taps (cols 0..31), b4 taps (cols 32..63)
+        for (int l = 0; l < B_LOADS; ++l) {
+          int col, drow;
+          if (l < 3) { col = 64; drow = l - 1; }
+          else if (l < 6) { col = 0; drow = l - 4; }
+          else { col = 32; drow = l - 8; }
+          mbar_wait(empty(slot), phase ^ 1u);
+          mbar_expect_tx(full(slot), B_SLOT_BYTES);
+          tma_load_2d(base + BSmem::ring + slot * B_SLOT_BYTES, &maps.t, full(slot), col, row0 + drow);
+          if (++slot == B_SLOTS) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0 && (int)blockIdx.x < num_tiles) {
+      const uint32_t id48 = idesc_f16(F16, 48), id64 = idesc_f16(F16, 64);
+      mbar_wait(wbar, 0);
+      int slot = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0, u_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * B_ACC_STRIDE;
+        auto run = [&](int ntaps, uint32_t w_off, uint32_t w_blk, uint32_t d, uint32_t idesc) {
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(full(slot), phase);
+            tc_fence_after();
+            const uint64_t ad = make_kmajor_desc<32>(base + BSmem::ring + slot * B_SLOT_BYTES);
+            const uint64_t bd = make_kmajor_desc<32>(base + w_off + t * w_blk);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) tc_mma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (t | k) != 0 ? 1u : 0u);
+            tc_commit(empty(slot));
+            if (++slot == B_SLOTS) { slot = 0; phase ^= 1u; }
+          }
+        };
+        run(3, BSmem::w5b, B_W64_BLK, d0 + 96, id64);
+        tc_commit(b5b_full(acc));
+        run(3, BSmem::w3, B_W48_BLK, d0, id48);
+        run(5, BSmem::w4, B_W48_BLK, d0 + 48, id48);
+        mbar_wait(u_full, u_phase);                       // relu(b5b) tile is in shared memory
+        u_phase ^= 1u;
+        tc_fence_after();
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t ad = make_kmajor_desc<32>(base + BSmem::u + kb * B_SLOT_BYTES);
+          const uint64_t bd = make_kmajor_desc<32>(base + BSmem::w5c + kb * B_W48_BLK);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) tc_mma_bf16(d0 + 160, ad + 2 * k, bd + 2 * k, id48, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(tfull(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ---------------- epilogue warps ----------------
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int i = q * 32 + lane;
+      const int row = tile * 128 + i;
+      const bool row_ok = row < p.M;
+      const bool halo = (row % p.Lp) >= p.L;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * B_ACC_STRIDE;
+      // ---- phase 1: relu(b5b + bias) -> 16-bit tile in shared memory (A operand of the 1x1 that follows) ----
+      mbar_wait(b5b_full(acc), acc_phase);
+      tc_fence_after();
+      {
+        uint32_t rr[2][16];
+        __syncwarp();
+        tc_ld16(t_row + 96u + (uint32_t)(half * 32), rr[0]);
+        tc_ld16(t_row + 96u + (uint32_t)(half * 32 + 16), rr[1]);
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int col = 96 + half * 32 + h2 * 16 + 2 * k;
+            float a = fmaxf(__uint_as_float(rr[h2][2 * k]) + sbias[col], 0.f);
+            float b = fmaxf(__uint_as_float(rr[h2][2 * k + 1]) + sbias[col + 1], 0.f);
+            if (halo || !row_ok) { a = 0.f; b = 0.f; }
+            pk[h2 * 8 + k] = pack16<F16>(a, b);
+          }
+        }
+        // k-block `half` of U: row i is 64 bytes; logical 16-byte chunk c sits at c ^ ((i >> 1) & 3)  (SWIZZLE_64B)
+        const uint32_t ub = base + BSmem::u + half * B_SLOT_BYTES + (uint32_t)i * 64u;
+        const uint32_t sw = (uint32_t)((i >> 1) & 3);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          sts128(ub + (((uint32_t)c ^ sw) << 4), make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(u_full);
+      }
+      // ---- phase 2: b3, b4, b5 = relu(stem + b5c) -> Y[:, 96:240] ----
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      for (int ch = half; ch < 9; ch += 2) {
+        const int grp = ch / 3, sub = ch % 3;                 // grp 0 b3, 1 b4, 2 b5c
+        const int tcol = (grp == 0 ? 0 : grp == 1 ? 48 : 160) + sub * 16;
+        const int ycol = 96 + grp * 48 + sub * 16;
+        uint32_t rr[16];
+        __syncwarp();
+        tc_ld16(t_row + (uint32_t)tcol, rr);
+        tc_wait_ld();
+        if (!row_ok) continue;
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 bb = *reinterpret_cast<const float4*>(sbias + tcol + 4 * k);
+          v[4 * k + 0] = __uint_as_float(rr[4 * k + 0]) + bb.x;
+          v[4 * k + 1] = __uint_as_float(rr[4 * k + 1]) + bb.y;
+          v[4 * k + 2] = __uint_as_float(rr[4 * k + 2]) + bb.z;
+          v[4 * k + 3] = __uint_as_float(rr[4 * k + 3]) + bb.w;
+        }
+        if (grp == 2) {                                        // residual: stem lives in T[:, 96:144]
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.T) + (size_t)row * p.ldT + 96 + sub * 16);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 rv = __ldg(rp + h);
+            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = unpack16<F16>(w[k]);
+              v[8 * h + 2 * k] += f.x;
+              v[8 * h + 2 * k + 1] += f.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = halo ? 0.f : fmaxf(v[k], 0.f);
+        uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.Y) + (size_t)row * p.ldY + ycol);
+        dp[0] = make_uint4(pack16<F16>(v[0], v[1]), pack16<F16>(v[2], v[3]), pack16<F16>(v[4], v[5]), pack16<F16>(v[6], v[7]));
+        dp[1] = make_uint4(pack16<F16>(v[8], v[9]), pack16<F16>(v[10], v[11]), pack16<F16>(v[12], v[13]), pack16<F16>(v[14], v[15]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <class K> void set_smem_once(K kern, bool* flags) {
+  int dev = 0;
+  DSB_CUDA(cudaGetDevice(&dev));
+  if (!flags[dev & 63]) {
+    DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    flags[dev & 63] = true;
+  }
+}
+
+}  // namespace
+
+void launch_incept_a(const InceptALaunch& L, int M, int sm_count, cudaStream_t s) {
+  if (M <= 0) return;
+  const int num_tiles = (M + INCEPT_A_TILE_ROWS - 1) / INCEPT_A_TILE_ROWS;
+  const int grid = num_tiles < sm_count ? num_tiles : sm_count;
+  InceptAParams p = L.p;
+  p.M = M;
+  const size_t smem = ASmem::total + 1024;
+  static bool cfg[2][64] = {{false}};
+  if (L.fp16) {
+    set_smem_once(incept_a_kernel<true>, cfg[1]);
+    incept_a_kernel<true><<<grid, A_THREADS, smem, s>>>(L.maps, p, num_tiles);
+  } else {
+    set_smem_once(incept_a_kernel<false>, cfg[0]);
+    incept_a_kernel<false><<<grid, A_THREADS, smem, s>>>(L.maps, p, num_tiles);
+  }
+  DSB_CUDA(cudaGetLastError());
+}
+
+void launch_incept_b(const InceptBLaunch& L, int M, int sm_count, cudaStream_t s) {
+  if (M <= 0) return;
+  const int num_tiles = (M + 127) / 128;
+  const int grid = num_tiles < sm_count ? num_tiles : sm_count;
+  InceptBParams p = L.p;
+  p.M = M;
+  const size_t smem = BSmem::total + 1024;
+  static bool cfg[2][64] = {{false}};
+  if (L.fp16) {
+    set_smem_once(incept_b_kernel<true>, cfg[1]);
+    incept_b_kernel<true><<<grid, B_THREADS, smem, s>>>(L.maps, p, num_tiles);
+  } else {
+    set_smem_once(incept_b_kernel<false>, cfg[0]);
+    incept_b_kernel<false><<<grid, B_THREADS, smem, s>>>(L.maps, p, num_tiles);
+  }
+  DSB_CUDA(cudaGetLastError());
+}
+
+}  // namespace dsb

@@ -1,0 +1,40 @@
+// incept_tc.cuh — interface of the two fused inception-block kernels (tcgen05 / TMA, sm_100a).
+//
+// One inception block (reference layers.py:87-139) = kernel A + kernel B:
+//   A  x -> { b1 = relu(conv1x1(maxpool3(x))), b2 = relu(conv1x1(x)) } -> Y[:, 0:96]
+//          { b3a | b4a | b5a = relu(conv1x1(x)), stem = conv1x1(x) }   -> T[:, 0:144]
+//      the 1x3 max pool is computed in shared memory from the x tile (in place, after the p1 MMAs consumed it)
+//   B  T -> b3 = relu(conv1x3(b3a)), b4 = relu(conv1x5(b4a)), b5 = relu(stem + conv1x1(relu(conv1x3(b5a)))) -> Y[:, 96:240]
+//      the intermediate [128 x 64] tile of branch 5 never leaves the SM (TMEM -> registers -> smem -> MMA)
+// HBM traffic per row: A 480 B in + 480 B out, B 288 B in + 288 B out (16-bit), against 4.3 KB for the seven
+// separate launches they replace.
+#pragma once
+#include "ops.cuh"
+
+namespace dsb {
+
+struct alignas(64) InceptAMaps { CUtensorMap x, wp1, wb1; };
+struct InceptAParams {
+  int M = 0, Lp = 0, L = 0;
+  int nkb = 4;                 // 64-wide K blocks of the input channels (256 or 240 -> 4)
+  void* Y = nullptr; int ldY = 0;
+  void* T = nullptr; int ldT = 0;
+  const float* bias = nullptr; // [240]: p1 (b2 48 | b3a 32 | b4a 32 | b5a 32 | stem 48) then b1 (48)
+};
+struct InceptALaunch { InceptAMaps maps; InceptAParams p; bool fp16 = false; };
+
+struct alignas(64) InceptBMaps { CUtensorMap t, w3, w4, w5b, w5c; };
+struct InceptBParams {
+  int M = 0, Lp = 0, L = 0;
+  const void* T = nullptr; int ldT = 0;
+  void* Y = nullptr; int ldY = 0;
+  const float* bias = nullptr; // [208]: b3 48 | b4 48 | b5b 64 | b5c 48
+};
+struct InceptBLaunch { InceptBMaps maps; InceptBParams p; bool fp16 = false; };
+
+constexpr int INCEPT_A_TILE_ROWS = 126;   // 128-row tiles overlap by one row on each side (pool halo)
+
+void launch_incept_a(const InceptALaunch& L, int M, int sm_count, cudaStream_t s);
+void launch_incept_b(const InceptBLaunch& L, int M, int sm_count, cudaStream_t s);
+
+}  // namespace dsb

@@ -187,3 +187,18 @@ def test_errors(engine, ckpt):
     with pytest.raises(DsbError):
         e2.load_weights(ckpt, is_cnn=False, is_rnn=False)
     e2.close()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_fused_inception_kernels_match_unfused_launches(engine, ckpt, precision, monkeypatch):
+    """The two fused inception kernels against the seven separate GEMM/pool launches they replace."""
+    x = _inputs(777, 110)
+    monkeypatch.setenv("DSB_FUSED", "0")
+    engine.load_weights(ckpt)              # plans are rebuilt after a weight load
+    a, pa = engine.forward(*x, precision=precision)
+    monkeypatch.setenv("DSB_FUSED", "1")
+    engine.load_weights(ckpt)
+    b, pb = engine.forward(*x, precision=precision)
+    d = np.abs(a - b).max()
+    print("\n[fused vs unfused, {}] max|dp|={:.3e} identical={}".format(precision, d, np.array_equal(a, b)))
+    assert d <= 1e-3
