@@ -142,29 +142,29 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
 
 // ---- maxpool 1x3 stride 1 SAME over rows (inputs >= 0, halo rows are zero) -------------------------
 template <class T>
-__global__ void pool3s1_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t M, int C) {
+__global__ void pool3s1_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t M, int C, int ld) {
   const int cv = C / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * cv) return;
   const int64_t r = idx / cv;
   const int c = (int)(idx % cv) * 8;
-  Vec8<T> a = Vec8<T>::load(x + r * C + c);
+  Vec8<T> a = Vec8<T>::load(x + r * ld + c);
   if (r > 0) {
-    const Vec8<T> b = Vec8<T>::load(x + (r - 1) * C + c);
+    const Vec8<T> b = Vec8<T>::load(x + (r - 1) * ld + c);
 #pragma unroll
     for (int i = 0; i < 8; ++i) a.v[i] = fmaxf(a.v[i], b.v[i]);
   }
   if (r + 1 < M) {
-    const Vec8<T> b = Vec8<T>::load(x + (r + 1) * C + c);
+    const Vec8<T> b = Vec8<T>::load(x + (r + 1) * ld + c);
 #pragma unroll
     for (int i = 0; i < 8; ++i) a.v[i] = fmaxf(a.v[i], b.v[i]);
   }
-  a.store(y + r * C + c);
+  a.store(y + r * ld + c);
 }
 
 // ---- maxpool 1x3 stride 2 SAME between stages (reference layers.py:211-213,224-226) ----------------
 template <class T>
-__global__ void pool3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, int C,
+__global__ void pool3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, int C, int ld,
                                int Lin, int Lpin, int Lout, int Lpout, int pl) {
   const int cv = C / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,12 +181,12 @@ __global__ void pool3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int64
     for (int k = 0; k < 3; ++k) {
       const int q = 2 * po - pl + k;
       if (q < 0 || q >= Lin) continue;
-      const Vec8<T> b = Vec8<T>::load(x + (s * Lpin + q) * C + c);
+      const Vec8<T> b = Vec8<T>::load(x + (s * Lpin + q) * ld + c);
 #pragma unroll
       for (int i = 0; i < 8; ++i) a.v[i] = fmaxf(a.v[i], b.v[i]);
     }
   }
-  a.store(y + ro * C + c);
+  a.store(y + ro * ld + c);
 }
 
 // ---- LSTM layer-0 feature rows: F[pos][n][FW] = onehot(code) | mean | std | len | 0... -------------
@@ -212,7 +212,7 @@ __global__ void lstm_feat_kernel(const int32_t* __restrict__ kmer, const float* 
 // (dense·dense_1 collapsed, avgpool folded into Wc; sigmoid + argmax fused; reference layers.py:250-264,
 // model.py:100,108).  One warp per sample.
 struct HeadParams {
-  const void* y; int Lp, L;           // final inception output [n*Lp][240] or nullptr
+  const void* y; int Lp, L, ldy;      // final inception output [n*Lp][ldy] (240 live channels) or nullptr
   const void* hfw; const void* hbw;   // [n][256] or nullptr
   const float* Wc;                    // [L*240][2]
   const float* Wr;                    // [512][2]
@@ -232,10 +232,10 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   for (int64_t s = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); s < p.n; s += (int64_t)gridDim.x * wpb) {
     float a0 = 0.f, a1 = 0.f;
     if (p.y != nullptr) {
-      const T* y = reinterpret_cast<const T*>(p.y) + s * p.Lp * CH;
-      const int nv = p.L * CH / 8;                 // contiguous: rows 0..L-1 of this sample
+      const T* y = reinterpret_cast<const T*>(p.y) + s * p.Lp * p.ldy;
+      const int nv = p.L * CH / 8;                 // rows 0..L-1 of this sample, 30 vectors of 8 channels per row
       for (int i = lane; i < nv; i += 32) {
-        const Vec8<T> v = Vec8<T>::load(y + i * 8);
+        const Vec8<T> v = Vec8<T>::load(y + (i / (CH / 8)) * p.ldy + (i % (CH / 8)) * 8);
         const float4* w = reinterpret_cast<const float4*>(hw + (size_t)i * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

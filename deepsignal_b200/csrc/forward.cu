@@ -36,7 +36,7 @@ struct Step {
   // helpers
   StemParams stem;
   const void* src = nullptr; void* dst = nullptr;
-  int C = 0, Lin = 0, Lpin = 0, Lout = 0, Lpout = 0, pl = 0;
+  int C = 0, ld = 0, Lin = 0, Lpin = 0, Lout = 0, Lpout = 0, pl = 0;
   size_t zero_bytes_per_sample = 0;
   HeadParams head;
 };
@@ -215,8 +215,13 @@ struct Builder {
       T* C2 = buf((size_t)R2 * 128);
       T* X0 = buf((size_t)R2 * 256);
       T* XP = buf((size_t)R2 * 256);
-      T* YA = buf((size_t)R2 * CH);
-      T* YB = buf((size_t)R2 * CH);
+      constexpr int YLD = 256;            // 240 channels padded to a 512-byte row pitch: every TMA row chunk is one aligned 128-byte line
+      T* YA = buf((size_t)R2 * YLD);
+      T* YB = buf((size_t)R2 * YLD);
+      T* TP3 = buf((size_t)R2 * 32);      // fused path: the block's 1x1 outputs as separate planes (contiguous TMA boxes)
+      T* TP4 = buf((size_t)R2 * 32);
+      T* TP5 = buf((size_t)R2 * 32);
+      T* TPS = buf((size_t)R2 * 48);
       T* Tb = buf((size_t)R2 * 144);
       T* Ub = buf((size_t)R2 * 64);
 
@@ -283,15 +288,17 @@ struct Builder {
               encode_map_16(&A.maps.x, X, rows_cap, cin, xld, 128, 64, f16);
               encode_map_16(&A.maps.wp1, Wp1.w, 192, Wp1.Ktot, Wp1.Ktot, 192, 64, f16);
               encode_map_16(&A.maps.wb1, Wb1.w, 48, Wb1.Ktot, Wb1.Ktot, 48, 64, f16);
-              A.p.Lp = Lp; A.p.L = L; A.p.Y = Y; A.p.ldY = CH; A.p.T = Tb; A.p.ldT = 144; A.p.bias = biasA;
+              A.p.Lp = Lp; A.p.L = L; A.p.Y = Y; A.p.ldY = YLD; A.p.P3 = TP3; A.p.P4 = TP4; A.p.P5 = TP5; A.p.PS = TPS; A.p.bias = biasA;
               InceptBLaunch& B = sb.ib;
               B.fp16 = f16;
-              encode_map_16(&B.maps.t, Tb, rows_cap, 144, 144, 128, 32, f16);
+              encode_map_16(&B.maps.t3, TP3, rows_cap, 32, 32, 128, 32, f16);
+              encode_map_16(&B.maps.t4, TP4, rows_cap, 32, 32, 128, 32, f16);
+              encode_map_16(&B.maps.t5, TP5, rows_cap, 32, 32, 128, 32, f16);
               encode_map_16(&B.maps.w3, Wb3.w, 48, Wb3.Ktot, Wb3.Ktot, 48, 32, f16);
               encode_map_16(&B.maps.w4, Wb4.w, 48, Wb4.Ktot, Wb4.Ktot, 48, 32, f16);
               encode_map_16(&B.maps.w5b, Wb5b.w, 64, Wb5b.Ktot, Wb5b.Ktot, 64, 32, f16);
               encode_map_16(&B.maps.w5c, Wb5c.w, 48, Wb5c.Ktot, Wb5c.Ktot, 48, 32, f16);
-              B.p.Lp = Lp; B.p.L = L; B.p.T = Tb; B.p.ldT = 144; B.p.Y = Y; B.p.ldY = CH; B.p.bias = biasB;
+              B.p.Lp = Lp; B.p.L = L; B.p.PS = TPS; B.p.Y = Y; B.p.ldY = YLD; B.p.bias = biasB;
             }
             plan.steps.push_back(sa);
             plan.steps.push_back(sb);
@@ -302,31 +309,31 @@ struct Builder {
             st.kind = ST_POOL1;
             st.stream = 0;
             st.rows_per_sample = Lp;
-            st.src = X; st.dst = XP; st.C = xld;
+            st.src = X; st.dst = XP; st.C = cin; st.ld = xld;
             plan.steps.push_back(st);
           }
-          gemm(0, Lp, rows_cap, {SegHost{XP, xld, cin, 0, 0, cin, Lp}}, Wb1, 64, conv_epi(Y, CH, 0, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, cin);
+          gemm(0, Lp, rows_cap, {SegHost{XP, xld, cin, 0, 0, cin, Lp}}, Wb1, 64, conv_epi(Y, YLD, 0, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, cin);
           {   // fused 1x1s: b2 -> Y[:,48:96] ; b3a|b4a|b5a|stem -> T[:,0:144] (stem without ReLU)
-            EpiParams e = conv_epi(Y, CH, 48, 0x1ffu /* cols 0..143 */, Lp, L);
+            EpiParams e = conv_epi(Y, YLD, 48, 0x1ffu /* cols 0..143 */, Lp, L);
             e.split = 48;
             e.d1 = Tb; e.ld1 = 144; e.c1 = 0;
             gemm(0, Lp, rows_cap, {SegHost{X, xld, cin, 0, 0, cin, Lp}}, Wp1, 64, e, EPI_CONV, KC_GEMM, L, cin);
           }
           gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 0, -1, 32, Lp}, SegHost{Tb, 144, 144, 0, 0, 32, Lp}, SegHost{Tb, 144, 144, 0, 1, 32, Lp}},
-               Wb3, 32, conv_epi(Y, CH, 96, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 96);
+               Wb3, 32, conv_epi(Y, YLD, 96, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 96);
           gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 32, -2, 32, Lp}, SegHost{Tb, 144, 144, 32, -1, 32, Lp}, SegHost{Tb, 144, 144, 32, 0, 32, Lp},
                                  SegHost{Tb, 144, 144, 32, 1, 32, Lp}, SegHost{Tb, 144, 144, 32, 2, 32, Lp}},
-               Wb4, 32, conv_epi(Y, CH, 144, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 160);
+               Wb4, 32, conv_epi(Y, YLD, 144, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 160);
           gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 64, -1, 32, Lp}, SegHost{Tb, 144, 144, 64, 0, 32, Lp}, SegHost{Tb, 144, 144, 64, 1, 32, Lp}},
                Wb5b, 32, conv_epi(Ub, 64, 0, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 96);
           {
-            EpiParams e = conv_epi(Y, CH, 192, 0xffffffffu, Lp, L);
+            EpiParams e = conv_epi(Y, YLD, 192, 0xffffffffu, Lp, L);
             e.res = Tb; e.res_ld = 144; e.res_c0 = 96;
             gemm(0, Lp, rows_cap, {SegHost{Ub, 64, 64, 0, 0, 64, Lp}}, Wb5c, 64, e, EPI_CONV, KC_GEMM, L, 64);
           }
         }
         X = Y;
-        xld = CH;
+        xld = YLD;
         T* other = (Y == YA) ? YB : YA;
         if (i == 2 || i == 7) {   // max pool 1x3 stride 2 between stages
           const int Lo = (i == 2) ? L3 : L4, Lpo = Lo + HALO;
@@ -334,7 +341,7 @@ struct Builder {
           Step st;
           st.kind = ST_POOL2;
           st.stream = 0;
-          st.src = Y; st.dst = other; st.C = CH; st.Lin = L; st.Lpin = Lp; st.Lout = Lo; st.Lpout = Lpo; st.pl = total / 2;
+          st.src = Y; st.dst = other; st.C = CH; st.ld = YLD; st.Lin = L; st.Lpin = Lp; st.Lout = Lo; st.Lpout = Lpo; st.pl = total / 2;
           plan.steps.push_back(st);
           X = other;
           other = Y;
@@ -412,7 +419,7 @@ struct Builder {
       Step st;
       st.kind = ST_HEAD;
       st.stream = 0;
-      st.head = HeadParams{final_y, final_Lp, fm.L4, hfw, hbw, Wc, Wr, nullptr, nullptr, 0};
+      st.head = HeadParams{final_y, final_Lp, fm.L4, 256, hfw, hbw, Wc, Wr, nullptr, nullptr, 0};
       plan.steps.push_back(st);
     }
   }
@@ -528,7 +535,7 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_POOL1: {
         Timer tm(ctx, s, KC_ELEM, 0);
         const int64_t total = M * (st.C / 8);
-        pool3s1_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), M, st.C);
+        pool3s1_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), M, st.C, st.ld);
         DSB_CUDA(cudaGetLastError());
         ctx->launches++;
         break;
@@ -536,7 +543,7 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_POOL2: {
         Timer tm(ctx, s, KC_ELEM, 0);
         const int64_t total = n * st.Lpout * (st.C / 8);
-        pool3s2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), n, st.C,
+        pool3s2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), n, st.C, st.ld,
                                                                           st.Lin, st.Lpin, st.Lout, st.Lpout, st.pl);
         DSB_CUDA(cudaGetLastError());
         ctx->launches++;

@@ -69,6 +69,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();        // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -268,8 +270,7 @@ void launch_one(const TcLaunch& L, int m_tiles, int grid, uint32_t tmem_cols, cu
     DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[dev & 63] = true;
   }
-  kern<<<grid, TC_THREADS, L.smem, s>>>(L.maps, L.p, m_tiles, tmem_cols);
-  DSB_CUDA(cudaGetLastError());
+  launch_pdl(kern, grid, TC_THREADS, L.smem, s, L.maps, L.p, m_tiles, tmem_cols);
 }
 
 }  // namespace

@@ -99,6 +99,8 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -131,30 +133,35 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
         mbar_wait(tempty(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_p1 = tmem_base + acc * A_ACC_STRIDE, d_b1 = d_p1 + 192;
-        int s = slot;
-        uint32_t ph = phase;
-        for (int j = 0; j < A_NKB; ++j) {               // p1: x tile straight from TMA
-          mbar_wait(full_x(s), ph);
-          tc_fence_after();
-          const uint64_t ad = make_kmajor_desc<64>(base + ASmem::ring + s * A_SLOT_BYTES);
-          const uint64_t bd = make_kmajor_desc<64>(base + ASmem::wp1 + j * A_WP1_BLK);
+        // software-pipelined issue order p1(0) p1(1) b1(0) p1(2) b1(1) p1(3) b1(2) b1(3): a slot is released one
+        // step after its p1 MMAs, so the TMA ring keeps most of its slots in flight.
+        int sp = slot, sb = slot;
+        uint32_t php = phase, phb = phase;
+        for (int step = 0; step <= A_NKB; ++step) {
+          if (step < A_NKB) {                              // p1: x tile straight from TMA
+            mbar_wait(full_x(sp), php);
+            tc_fence_after();
+            const uint64_t ad = make_kmajor_desc<64>(base + ASmem::ring + sp * A_SLOT_BYTES);
+            const uint64_t bd = make_kmajor_desc<64>(base + ASmem::wp1 + step * A_WP1_BLK);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_bf16(d_p1, ad + 2 * k, bd + 2 * k, id_p1, (j | k) != 0 ? 1u : 0u);
-          tc_commit(p1_done(s));
-          if (++s == A_SLOTS) { s = 0; ph ^= 1u; }
-        }
-        s = slot;
-        ph = phase;
-        for (int j = 0; j < A_NKB; ++j) {               // b1: the same slot after the pool warps rewrote it
-          mbar_wait(full_xp(s), ph);
-          tc_fence_after();
-          const uint64_t ad = make_kmajor_desc<64>(base + ASmem::ring + s * A_SLOT_BYTES);
-          const uint64_t bd = make_kmajor_desc<64>(base + ASmem::wb1 + j * A_WB1_BLK);
+            for (int k = 0; k < 4; ++k) tc_mma_bf16(d_p1, ad + 2 * k, bd + 2 * k, id_p1, (step | k) != 0 ? 1u : 0u);
+            tc_commit(p1_done(sp));
+            if (++sp == A_SLOTS) { sp = 0; php ^= 1u; }
+          }
+          if (step >= 1) {                                 // b1: the same slot after the pool warps rewrote it
+            const int j = step - 1;
+            mbar_wait(full_xp(sb), phb);
+            tc_fence_after();
+            const uint64_t ad = make_kmajor_desc<64>(base + ASmem::ring + sb * A_SLOT_BYTES);
+            const uint64_t bd = make_kmajor_desc<64>(base + ASmem::wb1 + j * A_WB1_BLK);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_bf16(d_b1, ad + 2 * k, bd + 2 * k, id_b1, (j | k) != 0 ? 1u : 0u);
-          tc_commit(empty(s));
-          if (++s == A_SLOTS) { s = 0; ph ^= 1u; }
+            for (int k = 0; k < 4; ++k) tc_mma_bf16(d_b1, ad + 2 * k, bd + 2 * k, id_b1, (j | k) != 0 ? 1u : 0u);
+            tc_commit(empty(sb));
+            if (++sb == A_SLOTS) { sb = 0; phb ^= 1u; }
+          }
         }
+        int s = sp;
+        uint32_t ph = php;
         slot = s;
         phase = ph;
         tc_commit(tfull(acc));
@@ -164,33 +171,39 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
     }
   } else if (warp < 6) {
     // ---------------- pool warps: maxpool 1x3 over rows, in place ----------------
-    const int r = threadIdx.x - 64;                      // tile row 0..127
-    const uint32_t sw = (uint32_t)(r & 7);
+    // thread -> (16-byte channel chunk c, group of 8 rows): ten row loads give eight pooled rows.
+    const int pt = threadIdx.x - 64;
+    const uint32_t c = (uint32_t)(pt & 7);
+    const int r0 = (pt >> 3) * 8;
     int slot = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int j = 0; j < A_NKB; ++j) {
         const uint32_t tb = base + ASmem::ring + slot * A_SLOT_BYTES;
         mbar_wait(full_x(slot), phase);
+        uint4 in[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          const int rr = r0 - 1 + k;
+          // logical 16-byte chunk c of row rr sits at physical chunk c ^ (rr & 7)  (SWIZZLE_128B)
+          if (rr >= 0 && rr < 128) in[k] = lds128(tb + (uint32_t)rr * 128u + ((c ^ (uint32_t)(rr & 7)) << 4));
+          else in[k] = make_uint4(0u, 0u, 0u, 0u);          // activations are >= 0: zero is neutral for max
+        }
         uint4 out[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          // logical 16-byte chunk c of row rr sits at physical chunk c ^ (rr & 7)  (SWIZZLE_128B)
-          uint4 v = lds128(tb + (uint32_t)r * 128u + (((uint32_t)c ^ sw) << 4));
-          if (r > 0) {
-            const uint4 u = lds128(tb + (uint32_t)(r - 1) * 128u + (((uint32_t)c ^ (uint32_t)((r - 1) & 7)) << 4));
-            v.x = max16x2<F16>(v.x, u.x); v.y = max16x2<F16>(v.y, u.y); v.z = max16x2<F16>(v.z, u.z); v.w = max16x2<F16>(v.w, u.w);
-          }
-          if (r < 127) {
-            const uint4 u = lds128(tb + (uint32_t)(r + 1) * 128u + (((uint32_t)c ^ (uint32_t)((r + 1) & 7)) << 4));
-            v.x = max16x2<F16>(v.x, u.x); v.y = max16x2<F16>(v.y, u.y); v.z = max16x2<F16>(v.z, u.z); v.w = max16x2<F16>(v.w, u.w);
-          }
-          out[c] = v;
+        for (int k = 0; k < 8; ++k) {
+          out[k].x = max16x2<F16>(max16x2<F16>(in[k].x, in[k + 1].x), in[k + 2].x);
+          out[k].y = max16x2<F16>(max16x2<F16>(in[k].y, in[k + 1].y), in[k + 2].y);
+          out[k].z = max16x2<F16>(max16x2<F16>(in[k].z, in[k + 1].z), in[k + 2].z);
+          out[k].w = max16x2<F16>(max16x2<F16>(in[k].w, in[k + 1].w), in[k + 2].w);
         }
         mbar_wait(p1_done(slot), phase);                 // the p1 MMAs have finished reading this slot
         named_bar_sync(1, 128);                          // every pool thread has finished reading its neighbours
 #pragma unroll
-        for (int c = 0; c < 8; ++c) sts128(tb + (uint32_t)r * 128u + (((uint32_t)c ^ sw) << 4), out[c]);
+        for (int k = 0; k < 8; ++k) {
+          const int rr = r0 + k;
+          sts128(tb + (uint32_t)rr * 128u + ((c ^ (uint32_t)(rr & 7)) << 4), out[k]);
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_xp(slot));
@@ -243,7 +256,10 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
           }
           uint16_t* dst;
           if (col < 48) dst = reinterpret_cast<uint16_t*>(p.Y) + (size_t)row * p.ldY + 48 + col;            // b2
-          else if (col < 192) dst = reinterpret_cast<uint16_t*>(p.T) + (size_t)row * p.ldT + (col - 48);    // b3a|b4a|b5a|stem
+          else if (col < 80) dst = reinterpret_cast<uint16_t*>(p.P3) + (size_t)row * 32 + (col - 48);       // b3a
+          else if (col < 112) dst = reinterpret_cast<uint16_t*>(p.P4) + (size_t)row * 32 + (col - 80);      // b4a
+          else if (col < 144) dst = reinterpret_cast<uint16_t*>(p.P5) + (size_t)row * 32 + (col - 112);     // b5a
+          else if (col < 192) dst = reinterpret_cast<uint16_t*>(p.PS) + (size_t)row * 48 + (col - 144);     // stem
           else dst = reinterpret_cast<uint16_t*>(p.Y) + (size_t)row * p.ldY + (col - 192);                  // b1
           uint4* dp = reinterpret_cast<uint4*>(dst);
           dp[0] = make_uint4(pack16<F16>(v[0], v[1]), pack16<F16>(v[2], v[3]), pack16<F16>(v[4], v[5]), pack16<F16>(v[6], v[7]));
@@ -269,7 +285,7 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
 // ============================================================================================
 // Kernel B
 // ============================================================================================
-constexpr int B_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int B_THREADS = 448;       // warp 0 TMA, warp 1 MMA, warps 2-5 branch-5 staging, warps 6-13 epilogue
 constexpr int B_SLOTS = 16;
 constexpr uint32_t B_SLOT_BYTES = 128 * 32 * 2;        // one [128 x 32] SWIZZLE_64B tile
 constexpr uint32_t B_W48_BLK = 48 * 32 * 2;            // 3072
@@ -282,11 +298,11 @@ struct BSmem {
   static constexpr uint32_t w4 = w3 + 3 * B_W48_BLK;
   static constexpr uint32_t w5b = w4 + 5 * B_W48_BLK;
   static constexpr uint32_t w5c = w5b + 3 * B_W64_BLK;
-  static constexpr uint32_t u = w5c + 2 * B_W48_BLK;          // 43008: two [128 x 32] blocks
-  static constexpr uint32_t ring = u + 2 * B_SLOT_BYTES;
+  static constexpr uint32_t u = w5c + 2 * B_W48_BLK;          // 43008: 2 stages x two [128 x 32] blocks
+  static constexpr uint32_t ring = u + 4 * B_SLOT_BYTES;
   static constexpr uint32_t bars = ring + B_SLOTS * B_SLOT_BYTES;
-  // barriers: full[S] empty[S] wbar b5b_full[2] u_full tfull[2] tempty[2]
-  static constexpr uint32_t nbars = 2 * B_SLOTS + 8;
+  // barriers: full[S] empty[S] wbar b5b_full[2] u_full[2] tfull[2] tempty[2]
+  static constexpr uint32_t nbars = 2 * B_SLOTS + 9;
   static constexpr uint32_t tmem_slot = (bars + 8 * nbars + 15u) & ~15u;
   static constexpr uint32_t bias = tmem_slot + 16;
   static constexpr uint32_t total = bias + 208 * 4;
@@ -302,17 +318,16 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
   auto empty = [&](int s) { return base + BSmem::bars + 8u * (B_SLOTS + s); };
   const uint32_t wbar = base + BSmem::bars + 8u * (2 * B_SLOTS);
   auto b5b_full = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + a); };
-  const uint32_t u_full = base + BSmem::bars + 8u * (2 * B_SLOTS + 3);
-  auto tfull = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 4 + a); };
-  auto tempty = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 6 + a); };
+  auto u_full = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 3 + a); };
+  auto tfull = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 5 + a); };
+  auto tempty = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 7 + a); };
   const uint32_t tmem_slot = base + BSmem::tmem_slot;
   float* sbias = reinterpret_cast<float*>(smem_raw + (base + BSmem::bias - smem_u32(smem_raw)));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < B_SLOTS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     mbar_init(wbar, 1);
-    mbar_init(u_full, 8);
-    for (int a = 0; a < 2; ++a) { mbar_init(b5b_full(a), 1); mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(b5b_full(a), 1); mbar_init(u_full(a), 4); mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 208; i += B_THREADS) sbias[i] = p.bias[i];
@@ -325,6 +340,8 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -338,15 +355,16 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * 128;
-        // order of consumption: b5b taps (T cols 64..95), b3 taps (cols 0..31), b4 taps (cols 32..63)
+        // order of consumption: b5b taps (plane P5), b3 taps (P3), b4 taps (P4)
         for (int l = 0; l < B_LOADS; ++l) {
-          int col, drow;
-          if (l < 3) { col = 64; drow = l - 1; }
-          else if (l < 6) { col = 0; drow = l - 4; }
-          else { col = 32; drow = l - 8; }
+          const CUtensorMap* mp;
+          int drow;
+          if (l < 3) { mp = &maps.t5; drow = l - 1; }
+          else if (l < 6) { mp = &maps.t3; drow = l - 4; }
+          else { mp = &maps.t4; drow = l - 8; }
           mbar_wait(empty(slot), phase ^ 1u);
           mbar_expect_tx(full(slot), B_SLOT_BYTES);
-          tma_load_2d(base + BSmem::ring + slot * B_SLOT_BYTES, &maps.t, full(slot), col, row0 + drow);
+          tma_load_2d(base + BSmem::ring + slot * B_SLOT_BYTES, mp, full(slot), 0, row0 + drow);
           if (++slot == B_SLOTS) { slot = 0; phase ^= 1u; }
         }
       }
@@ -357,7 +375,7 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
       const uint32_t id48 = idesc_f16(F16, 48), id64 = idesc_f16(F16, 64);
       mbar_wait(wbar, 0);
       int slot = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0, u_phase = 0;
+      uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty(acc), acc_phase ^ 1u);
         tc_fence_after();
@@ -378,11 +396,10 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
         tc_commit(b5b_full(acc));
         run(3, BSmem::w3, B_W48_BLK, d0, id48);
         run(5, BSmem::w4, B_W48_BLK, d0 + 48, id48);
-        mbar_wait(u_full, u_phase);                       // relu(b5b) tile is in shared memory
-        u_phase ^= 1u;
+        mbar_wait(u_full(acc), acc_phase);                // relu(b5b) tile of this stage is in shared memory
         tc_fence_after();
         for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t ad = make_kmajor_desc<32>(base + BSmem::u + kb * B_SLOT_BYTES);
+          const uint64_t ad = make_kmajor_desc<32>(base + BSmem::u + (2 * acc + kb) * B_SLOT_BYTES);
           const uint64_t bd = make_kmajor_desc<32>(base + BSmem::w5c + kb * B_W48_BLK);
 #pragma unroll
           for (int k = 0; k < 2; ++k) tc_mma_bf16(d0 + 160, ad + 2 * k, bd + 2 * k, id48, (kb | k) != 0 ? 1u : 0u);
@@ -392,10 +409,56 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else {
-    // ---------------- epilogue warps ----------------
+  } else if (warp < 6) {
+    // ---------------- branch-5 staging warps: relu(b5b + bias) -> 16-bit A operand of the 1x1 that follows ----------------
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int i = q * 32 + lane;
+      const int row = tile * 128 + i;
+      const bool zero = row >= p.M || (row % p.Lp) >= p.L;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * B_ACC_STRIDE + 96u;
+      mbar_wait(b5b_full(acc), acc_phase);
+      tc_fence_after();
+      uint32_t rr[4][16];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tc_ld16(t_row + 16u * g, rr[g]);
+      tc_wait_ld();
+      const uint32_t sw = (uint32_t)((i >> 1) & 3);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        // k-block kb of U: row i is 64 bytes; logical 16-byte chunk c sits at c ^ ((i >> 1) & 3)  (SWIZZLE_64B)
+        const uint32_t ub = base + BSmem::u + (2 * acc + kb) * B_SLOT_BYTES + (uint32_t)i * 64u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[4];
+          const int e0 = kb * 32 + c * 8;                      // first b5b output channel of this 16-byte chunk
+          const float4 b0 = *reinterpret_cast<const float4*>(sbias + 96 + e0);
+          const float4 b1 = *reinterpret_cast<const float4*>(sbias + 96 + e0 + 4);
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int e = e0 + 2 * k;
+            float a = fmaxf(__uint_as_float(rr[e >> 4][e & 15]) + bv[2 * k], 0.f);
+            float b = fmaxf(__uint_as_float(rr[(e + 1) >> 4][(e + 1) & 15]) + bv[2 * k + 1], 0.f);
+            if (zero) { a = 0.f; b = 0.f; }
+            pk[k] = pack16<F16>(a, b);
+          }
+          sts128(ub + (((uint32_t)c ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(u_full(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else {
+    // ---------------- epilogue warps: b3, b4, b5 = relu(stem + b5c) -> Y[:, 96:240] ----------------
+    const int q = warp & 3;
+    const int half = (warp - 6) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -404,38 +467,16 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
       const bool row_ok = row < p.M;
       const bool halo = (row % p.Lp) >= p.L;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * B_ACC_STRIDE;
-      // ---- phase 1: relu(b5b + bias) -> 16-bit tile in shared memory (A operand of the 1x1 that follows) ----
-      mbar_wait(b5b_full(acc), acc_phase);
-      tc_fence_after();
+      // the residual (stem plane) is an input: fetch it before waiting for the accumulators
+      uint4 res[2][2];
       {
-        uint32_t rr[2][16];
-        __syncwarp();
-        tc_ld16(t_row + 96u + (uint32_t)(half * 32), rr[0]);
-        tc_ld16(t_row + 96u + (uint32_t)(half * 32 + 16), rr[1]);
-        tc_wait_ld();
-        uint32_t pk[16];
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int col = 96 + half * 32 + h2 * 16 + 2 * k;
-            float a = fmaxf(__uint_as_float(rr[h2][2 * k]) + sbias[col], 0.f);
-            float b = fmaxf(__uint_as_float(rr[h2][2 * k + 1]) + sbias[col + 1], 0.f);
-            if (halo || !row_ok) { a = 0.f; b = 0.f; }
-            pk[h2 * 8 + k] = pack16<F16>(a, b);
-          }
-        }
-        // k-block `half` of U: row i is 64 bytes; logical 16-byte chunk c sits at c ^ ((i >> 1) & 3)  (SWIZZLE_64B)
-        const uint32_t ub = base + BSmem::u + half * B_SLOT_BYTES + (uint32_t)i * 64u;
-        const uint32_t sw = (uint32_t)((i >> 1) & 3);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          sts128(ub + (((uint32_t)c ^ sw) << 4), make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(u_full);
+        const uint16_t* tp = reinterpret_cast<const uint16_t*>(p.PS) + (size_t)(row_ok ? row : 0) * 48;
+        const int s0 = half == 0 ? 0 : 1, s1 = 2;             // grp-2 sub-chunks of this warp set: {0, 2} or {1}
+        res[0][0] = __ldg(reinterpret_cast<const uint4*>(tp + s0 * 16));
+        res[0][1] = __ldg(reinterpret_cast<const uint4*>(tp + s0 * 16) + 1);
+        res[1][0] = __ldg(reinterpret_cast<const uint4*>(tp + s1 * 16));
+        res[1][1] = __ldg(reinterpret_cast<const uint4*>(tp + s1 * 16) + 1);
       }
-      // ---- phase 2: b3, b4, b5 = relu(stem + b5c) -> Y[:, 96:240] ----
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
       for (int ch = half; ch < 9; ch += 2) {
@@ -456,11 +497,10 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
           v[4 * k + 2] = __uint_as_float(rr[4 * k + 2]) + bb.z;
           v[4 * k + 3] = __uint_as_float(rr[4 * k + 3]) + bb.w;
         }
-        if (grp == 2) {                                        // residual: stem lives in T[:, 96:144]
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.T) + (size_t)row * p.ldT + 96 + sub * 16);
+        if (grp == 2) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const uint4 rv = __ldg(rp + h);
+            const uint4 rv = (sub == 2) ? res[1][h] : res[0][h];
             const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -513,10 +553,10 @@ void launch_incept_a(const InceptALaunch& L, int M, int sm_count, cudaStream_t s
   static bool cfg[2][64] = {{false}};
   if (L.fp16) {
     set_smem_once(incept_a_kernel<true>, cfg[1]);
-    incept_a_kernel<true><<<grid, A_THREADS, smem, s>>>(L.maps, p, num_tiles);
+    launch_pdl(incept_a_kernel<true>, grid, A_THREADS, smem, s, L.maps, p, num_tiles);
   } else {
     set_smem_once(incept_a_kernel<false>, cfg[0]);
-    incept_a_kernel<false><<<grid, A_THREADS, smem, s>>>(L.maps, p, num_tiles);
+    launch_pdl(incept_a_kernel<false>, grid, A_THREADS, smem, s, L.maps, p, num_tiles);
   }
   DSB_CUDA(cudaGetLastError());
 }
@@ -531,10 +571,10 @@ void launch_incept_b(const InceptBLaunch& L, int M, int sm_count, cudaStream_t s
   static bool cfg[2][64] = {{false}};
   if (L.fp16) {
     set_smem_once(incept_b_kernel<true>, cfg[1]);
-    incept_b_kernel<true><<<grid, B_THREADS, smem, s>>>(L.maps, p, num_tiles);
+    launch_pdl(incept_b_kernel<true>, grid, B_THREADS, smem, s, L.maps, p, num_tiles);
   } else {
     set_smem_once(incept_b_kernel<false>, cfg[0]);
-    incept_b_kernel<false><<<grid, B_THREADS, smem, s>>>(L.maps, p, num_tiles);
+    launch_pdl(incept_b_kernel<false>, grid, B_THREADS, smem, s, L.maps, p, num_tiles);
   }
   DSB_CUDA(cudaGetLastError());
 }

@@ -2,7 +2,7 @@
 //
 // One inception block (reference layers.py:87-139) = kernel A + kernel B:
 //   A  x -> { b1 = relu(conv1x1(maxpool3(x))), b2 = relu(conv1x1(x)) } -> Y[:, 0:96]
-//          { b3a | b4a | b5a = relu(conv1x1(x)), stem = conv1x1(x) }   -> T[:, 0:144]
+//          { b3a | b4a | b5a = relu(conv1x1(x)), stem = conv1x1(x) }   -> planes P3, P4, P5 [M][32], PS [M][48]
 //      the 1x3 max pool is computed in shared memory from the x tile (in place, after the p1 MMAs consumed it)
 //   B  T -> b3 = relu(conv1x3(b3a)), b4 = relu(conv1x5(b4a)), b5 = relu(stem + conv1x1(relu(conv1x3(b5a)))) -> Y[:, 96:240]
 //      the intermediate [128 x 64] tile of branch 5 never leaves the SM (TMEM -> registers -> smem -> MMA)
@@ -18,15 +18,16 @@ struct InceptAParams {
   int M = 0, Lp = 0, L = 0;
   int nkb = 4;                 // 64-wide K blocks of the input channels (256 or 240 -> 4)
   void* Y = nullptr; int ldY = 0;
-  void* T = nullptr; int ldT = 0;
+  void* P3 = nullptr; void* P4 = nullptr; void* P5 = nullptr;   // [M][32] planes: b3a, b4a, b5a
+  void* PS = nullptr;                                           // [M][48] plane: residual stem
   const float* bias = nullptr; // [240]: p1 (b2 48 | b3a 32 | b4a 32 | b5a 32 | stem 48) then b1 (48)
 };
 struct InceptALaunch { InceptAMaps maps; InceptAParams p; bool fp16 = false; };
 
-struct alignas(64) InceptBMaps { CUtensorMap t, w3, w4, w5b, w5c; };
+struct alignas(64) InceptBMaps { CUtensorMap t3, t4, t5, w3, w4, w5b, w5c; };
 struct InceptBParams {
   int M = 0, Lp = 0, L = 0;
-  const void* T = nullptr; int ldT = 0;
+  const void* PS = nullptr;    // [M][48] residual stem plane
   void* Y = nullptr; int ldY = 0;
   const float* bias = nullptr; // [208]: b3 48 | b4 48 | b5b 64 | b5c 48
 };

@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <utility>
+
 #include "ops.cuh"
 
 namespace dsb {
@@ -103,5 +105,27 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Programmatic dependent launch: let the next kernel of the stream start its prologue while this grid drains,
+// and wait for the previous grid's results before touching them.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace tc
+
+// Host: launch with the programmatic-stream-serialization attribute (kernels call pdl_wait_prior_grid()).
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  DSB_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+}
+
 }  // namespace dsb
