@@ -473,6 +473,14 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
   const FoldedModel& fm = ctx->model;
   const bool multi = plan.multi_stream && !ctx->prof.enabled && fm.has_rnn() && fm.has_cnn();
   cudaStream_t streams[3] = {main_stream, multi ? plan.side[0] : main_stream, multi ? plan.side[1] : main_stream};
+  // SM budget per stream: the persistent kernels size their grids to it, so the LSTM stream (L2-bound) and the
+  // CNN stream (HBM-bound) can run side by side instead of time-slicing whole-GPU grids.
+  static const int lstm_sms_env = getenv("DSB_LSTM_SMS") ? atoi(getenv("DSB_LSTM_SMS")) : 0;
+  int sms[3] = {ctx->sm_count, ctx->sm_count, ctx->sm_count};
+  if (multi && lstm_sms_env > 0 && lstm_sms_env < ctx->sm_count / 2) {
+    sms[1] = sms[2] = lstm_sms_env;
+    sms[0] = ctx->sm_count - 2 * lstm_sms_env;
+  }
   bool forked = false;
   static const bool debug_sync = getenv("DSB_DEBUG_SYNC") != nullptr;
   int step_idx = -1;
@@ -500,7 +508,7 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
           g.rows_valid = (int)M;
           launch_gemm_f32(g, st.epi_kind, s);
         } else {
-          launch_gemm_tc(st.tc, (int)M, ctx->sm_count, s);
+          launch_gemm_tc(st.tc, (int)M, sms[st.stream], s);
         }
         ctx->launches++;
         break;
@@ -508,7 +516,7 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_INCEPT_A: {
         if constexpr (!std::is_same<T, float>::value) {
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
-          launch_incept_a(st.ia, (int)M, ctx->sm_count, s);
+          launch_incept_a(st.ia, (int)M, sms[st.stream], s);
           ctx->launches++;
         }
         break;
@@ -516,7 +524,7 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_INCEPT_B: {
         if constexpr (!std::is_same<T, float>::value) {
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
-          launch_incept_b(st.ib, (int)M, ctx->sm_count, s);
+          launch_incept_b(st.ib, (int)M, sms[st.stream], s);
           ctx->launches++;
         }
         break;

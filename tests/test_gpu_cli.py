@@ -1,0 +1,85 @@
+"""End-to-end drop-in checks on the GPU: the `deepsignal extract` / `deepsignal call_mods` commands
+produce the reference's file formats; extraction text is identical to the oracle's, called
+probabilities agree with the float64 oracle within the path's tolerance."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from deepsignal_b200 import weights as W
+from deepsignal_b200.synth import CONTIGS, synth_features, synth_reads, write_feature_tsv
+from deepsignal_b200.extract_features import save_reads
+from oracle import features_oracle as fo
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    r = subprocess.run([sys.executable, "-m", "deepsignal_b200.deepsignal"] + list(args), cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def test_extract_cli_text_identical_to_oracle(tmp_path):
+    rb = synth_reads(24, seed=31, nb_lo=300, nb_hi=900, cg_frac=0.03)
+    reads_p = str(tmp_path / "reads.npz")
+    save_reads(reads_p, rb)
+    ref_fa = str(tmp_path / "ref.fa")
+    with open(ref_fa, "w") as fh:
+        for name, n in CONTIGS.items():
+            fh.write(">%s synthetic\n" % name)
+            fh.write("N" * 10 + "\n")          # lengths come from the file: make them differ from CONTIGS
+    out = str(tmp_path / "features.tsv")
+    _run("extract", "-i", reads_p, "-o", out, "--reference_path", ref_fa, "--motifs", "CG", "--mod_loc", "0")
+    want = []
+    for i in range(rb.n_reads):
+        want += [fo.features_to_str(f) for f in fo.extract_read(rb.read_dict(i), ["CG"], 0, {k: 10 for k in CONTIGS})]
+    got = open(out).read().splitlines()
+    assert len(got) == len(want) and len(got) > 50
+    assert got == want                     # every float prints identically: the float64 features are bit-exact
+
+
+def test_call_mods_cli_from_feature_file_and_from_reads(tmp_path):
+    ck = W.random_checkpoint(17, "stress")
+    model_p = str(tmp_path / "bn_17.sn_360.epoch_0.ckpt.npz")
+    W.save_npz(model_p, ck)
+    f = synth_features(300, seed=41, sites_per_read=7)
+    feats_p = str(tmp_path / "features.tsv")
+    write_feature_tsv(feats_p, f)
+    res_p = str(tmp_path / "calls.tsv")
+    _run("call_mods", "-i", feats_p, "-m", model_p, "-o", res_p, "--precision", "fp32", "--f5_batch_num", "3")
+    lines = open(res_p).read().splitlines()
+    assert len(lines) == 300
+    ref, ref_pred = mo.forward(ck, f["kmer"], f["means"], f["stds"], f["lens"], f["signals"])
+    p0n, p1n = mo.host_normalise(ref)
+    for i, ln in enumerate(lines):
+        c = ln.split("\t")
+        assert len(c) == 10
+        assert c[4] == "read_%06d" % f["read_index"][i] and c[9] == "".join("ACGTN"[k] for k in f["kmer"][i])
+        assert abs(float(c[6]) - p0n[i]) <= 2e-4 and abs(float(c[7]) - p1n[i]) <= 2e-4
+        if abs(ref[i, 0] - ref[i, 1]) > 1e-3:
+            assert int(c[8]) == ref_pred[i]
+    # fast5-directory mode of the reference == packed reads here: extraction and forward fused on the GPU
+    rb = synth_reads(10, seed=42, nb_lo=300, nb_hi=700, cg_frac=0.03)
+    reads_p = str(tmp_path / "reads.npz")
+    save_reads(reads_p, rb)
+    res2 = str(tmp_path / "calls2.tsv")
+    _run("call_mods", "-i", reads_p, "-m", model_p, "-o", res2, "--precision", "fp32")
+    feats = []
+    for i in range(rb.n_reads):
+        feats += fo.extract_read(rb.read_dict(i), ["CG"])
+    lines2 = open(res2).read().splitlines()
+    assert len(lines2) == len(feats) and len(feats) > 20
+    kmer = np.asarray([[fo_code for fo_code in map("ACGTN".index, ft[6])] for ft in feats], np.int32)
+    ref2, _ = mo.forward(ck, kmer, np.asarray([ft[7] for ft in feats]), np.asarray([ft[8] for ft in feats]),
+                         np.asarray([ft[9] for ft in feats], np.float64), np.asarray([ft[10] for ft in feats]))
+    q0, _ = mo.host_normalise(ref2)
+    for i, ln in enumerate(lines2):
+        c = ln.split("\t")
+        assert c[1] == str(feats[i][1]) and c[4] == feats[i][4] and c[3] == "-1"
+        assert abs(float(c[6]) - q0[i]) <= 2e-4

@@ -1,0 +1,136 @@
+"""CPU tests of the host-side mirror of the reference interface (feature-file parsing, result
+formatting, CLI flags, read sharding) — no GPU and no oracle compute involved except as data."""
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from deepsignal_b200 import call_modifications as cm
+from deepsignal_b200 import extract_features as ef
+from deepsignal_b200 import parallel
+from oracle import features_oracle as fo
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class ListQ(list):
+    def put(self, x):
+        self.append(x)
+
+
+def test_read_features_file_matches_reference(golden):
+    a, m = golden
+    q = ListQ()
+    cm._read_features_file(os.path.join(GOLDEN, "features_small.tsv"), q, f5_batch_num=2)
+    assert q[-1] == "kill"
+    assert [len(b[0]) for b in q[:-1]] == m["tsv_batches"]
+    b0 = q[0]
+    assert b0[0] == m["tsv_b0_sampleinfo"]
+    assert np.array_equal(np.asarray(b0[1], np.int32), a["tsv_b0_kmers"])
+    assert np.array_equal(np.asarray(b0[2]), a["tsv_b0_means"])
+    assert np.array_equal(np.asarray(b0[4]), a["tsv_b0_lens"])
+    assert np.array_equal(np.asarray(b0[5]), a["tsv_b0_signals"])
+
+
+def test_call_mods_formatting_matches_reference(golden):
+    """The reference's _call_mods with a fake session gave golden pred_str; ours with a fake engine must too."""
+    a, m = golden
+    q = ListQ()
+    cm._read_features_file(os.path.join(GOLDEN, "features_small.tsv"), q, f5_batch_num=2)
+    fake = a["call_fake_probs"]
+
+    class FakeEngine(object):
+        def forward(self, kmer, means, stds, lens, signals, precision="fp16"):
+            n = len(kmer)
+            assert means.dtype == np.float32 and lens.dtype == np.float32 and signals.shape == (n, 360)
+            return fake[:n], np.argmax(fake[:n], axis=1).astype(np.int32)
+
+    model = cm._ModelHandle(17, 360, 2)
+    pred_str, acc, nb = cm._call_mods(q[0], FakeEngine(), model, 0.001, 512)
+    assert pred_str == m["call_pred_str"]
+    assert nb == 1 and 0.0 <= acc <= 1.0
+    cols = pred_str[0].split("\t")
+    assert len(cols) == 10 and cols[6] == "0.5" and cols[8] == "0"      # tie -> class 0
+
+
+def test_features_to_str_matches_reference(golden, golden_reads):
+    _, m = golden
+    from deepsignal_b200.synth import CONTIGS
+    feats = []
+    for i in range(golden_reads.n_reads):
+        feats += fo.extract_read(golden_reads.read_dict(i), ["CG"], 0, dict(CONTIGS))
+    assert [ef._features_to_str(f) for f in feats[:8]] == m["extract_tsv"]
+    assert len(m["extract_tsv"][0].split("\t")) == 12
+
+
+def test_reads_container_roundtrip(tmp_path, golden_reads):
+    p = str(tmp_path / "reads.npz")
+    ef.save_reads(p, golden_reads)
+    rb = ef.load_reads(p, chrom2len={"chrSynA": 5_000_000})
+    assert rb.n_reads == golden_reads.n_reads and rb.read_id == golden_reads.read_id
+    assert np.array_equal(rb.raw, golden_reads.raw) and np.array_equal(rb.ev_off, golden_reads.ev_off)
+    assert set(rb.chrom_len.tolist()) <= {5_000_000, -1}
+    rb2 = ef.load_reads(str(tmp_path))
+    assert rb2.n_reads == rb.n_reads and np.all(rb2.chrom_len == -1)
+    part = ef._concat_reads([golden_reads.slice(0, 2), golden_reads.slice(2, golden_reads.n_reads)])
+    assert np.array_equal(part.raw_off, golden_reads.raw_off) and np.array_equal(part.ev_start, golden_reads.ev_start)
+
+
+def test_cli_flags_and_defaults(monkeypatch):
+    from deepsignal_b200 import deepsignal as cli
+    seen = {}
+    monkeypatch.setattr(cli, "main_extraction", lambda args: seen.update(extract=args))
+    monkeypatch.setattr(cli, "main_call_mods", lambda args: seen.update(call=args))
+    # set_defaults binds the functions at parser-build time, so patch before main() builds it
+    monkeypatch.setattr(sys, "argv", ["deepsignal", "extract", "-i", "d", "-o", "o.tsv"])
+    cli.main()
+    e = seen["extract"]
+    assert (e.kmer_len, e.cent_signals_len, e.motifs, e.mod_loc, e.normalize_method, e.methy_label) == (17, 360, "CG", 0, "mad", 1)
+    assert (e.corrected_group, e.basecall_subgroup, e.recursively, e.is_dna, e.w_is_dir, e.w_batch_num, e.f5_batch_num, e.nproc) == \
+        ("RawGenomeCorrected_000", "BaseCalled_template", "yes", "yes", "no", 200, 50, 1)
+    monkeypatch.setattr(sys, "argv", ["deepsignal", "call_mods", "-i", "f.tsv", "-m", "m.ckpt", "-o", "r.tsv"])
+    cli.main()
+    c = seen["call"]
+    assert (c.kmer_len, c.cent_signals_len, c.batch_size, c.learning_rate, c.class_num, c.is_gpu) == (17, 360, 512, 0.001, 2, "no")
+    assert (c.is_cnn, c.is_rnn, c.is_base, c.f5_batch_num, c.precision) == ("yes", "yes", "yes", 50, "fp16")
+
+
+def test_shard_ranges_cover_without_overlap():
+    for n in (0, 1, 7, 8, 1000003):
+        for w in (1, 2, 3, 8):
+            spans = [parallel.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world_size, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    n_reads = 11
+    lo, hi = parallel.shard_range(n_reads, rank, world_size)
+    # every rank "calls" its reads: two result lines per read, reads stay contiguous
+    local = [(r, ["read%d\tline%d" % (r, k) for k in range(2)]) for r in range(lo, hi)]
+    merged = parallel.gather_in_order(local, rank, world_size)
+    if rank == 0:
+        with open(os.path.join(out_dir, "merged.txt"), "w") as fh:
+            for lines in merged:
+                fh.write("\n".join(lines) + "\n")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_host_gather(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = open(os.path.join(str(tmp_path), "merged.txt")).read().splitlines()
+    assert got == ["read%d\tline%d" % (r, k) for r in range(11) for k in range(2)]
