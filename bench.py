@@ -127,6 +127,66 @@ def device_inputs(torch, n, dev, seed):
     return kmer.contiguous(), means.contiguous(), stds.contiguous(), lens.contiguous(), signals.contiguous()
 
 
+def bench_reads(a, eng, torch, dev, rank, world, barrier, max_over_ranks, ckpt):
+    """configs[1] (extraction only) and configs[3] (extraction + forward) on synthetic resquiggled reads."""
+    from deepsignal_b200.synth import synth_reads, SEED_CFG2, SEED_CFG4
+    from oracle import features_oracle as fo
+    rb = synth_reads(a.reads, seed=(SEED_CFG2 if a.workload == "extract" else SEED_CFG4) + rank)
+    dr = eng.reads_to_device(rb, dev)
+    n_raw, n_ev = int(rb.raw_off[-1]), int(rb.ev_off[-1])
+    cap = max(1024, int(n_ev * 0.03))
+    bufs = eng.alloc_site_bufs(cap, dev)
+
+    def step():
+        if a.workload == "extract":
+            return eng.extract_torch(dr, rb.n_reads, bufs)
+        return eng.extract_call_torch(dr, rb.n_reads, precision=a.precision, site_bufs=bufs)[0]
+
+    for _ in range(a.warmup):
+        n_sites = step()
+    sampler = ClockSampler(torch.cuda.current_device())
+    barrier()
+    sampler.start()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        n_sites = step()
+    e1.record()
+    barrier()
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    sites_s = world * n_sites * a.steps / (ms * 1e-3)
+    alg_bytes = 2.0 * n_raw + 9.0 * n_ev + 1677.0 * n_sites          # SURVEY §8d per-read figure
+    pk = peaks()
+    out = {
+        "metric": "CpG samples/sec ({})".format("extract_features" if a.workload == "extract" else "extract + call_mods"),
+        "value": sites_s, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if a.workload == "extract" else a.precision, "data": "synthetic",
+        "config": {"workload": "BASELINE configs[{}]: {} synthetic tombo-style R9.4 reads per GPU, {} raw samples, {} bases, {} CpG sites".format(
+            1 if a.workload == "extract" else 3, rb.n_reads, n_raw, n_ev, n_sites),
+            "reads_per_s": world * rb.n_reads * a.steps / (ms * 1e-3),
+            "l2": "raw signal {} MB + outputs {} MB per step exceed the 126 MB L2".format(2 * n_raw >> 20, int(1677 * n_sites) >> 20)},
+        "clocks": clocks, "gpu_launches": int(launches)}
+    if a.workload == "extract":
+        ach = alg_bytes * a.steps / (ms * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                           "traffic": None, "kernel": "extraction kernel chain (5 launches per batch)",
+                           "peak_source": pk["source"]}
+        if rank == 0 and not a.no_cpu_baseline:
+            k = min(rb.n_reads, 40)
+            t0 = time.perf_counter()
+            ns = 0
+            for i in range(k):
+                ns += len(fo.extract_read(rb.read_dict(i), ["CG"]))
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": ns / dt, "unit": "samples/s", "cores": 1, "kind": "port",
+                                   "sample": "{} reads ({} sites) through the NumPy restatement of _extract_features, {:.1f} s".format(k, ns, dt)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -139,6 +199,10 @@ def main():
     ap.add_argument("--max-chunk", type=int, default=16384)
     ap.add_argument("--cpu-samples", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="forward", choices=["forward", "extract", "e2e"],
+                    help="forward = BASELINE configs[2] (default, the metric's workload); extract = configs[1] "
+                         "(4k reads, extraction only); e2e = configs[3] (extract + call_mods, read-sharded)")
+    ap.add_argument("--reads", type=int, default=4000)
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
@@ -198,6 +262,14 @@ def main():
     eng = Engine(local_rank)
     eng.load_weights(ckpt)
     eng.set_max_chunk(a.max_chunk)
+    if a.workload != "forward":
+        out = bench_reads(a, eng, torch, dev, rank, world, barrier, max_over_ranks, ckpt)
+        if rank == 0:
+            print(json.dumps(out))
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     n = a.samples_per_step
     x = device_inputs(torch, n, dev, 20260103 + rank)
     probs = torch.empty((n, 2), dtype=torch.float32, device=dev)

@@ -20,6 +20,7 @@ namespace dsb {
 
 struct ExtractWork {
   DevBuf base_mean, base_std, base_len, counts, offsets, shift, scale, scratch, total, tmp_read, tmp_loc;
+  DevBuf vmin, bins, lut_off, lut;
 };
 void destroy_extract(ExtractWork* p) { delete p; }
 
@@ -55,6 +56,7 @@ template <class T> __device__ __forceinline__ T block_reduce(T v, T* sh, bool is
 struct NormParams {
   const int16_t* raw; const int64_t* raw_off; const double* scaling; const double* offset;
   int64_t R; int method; double* shift; double* scale; uint32_t* gscratch;
+  int32_t* vmin; int64_t* bins;      // per-read raw minimum and number of distinct-value bins (LUT size)
 };
 
 __global__ void __launch_bounds__(NORM_THREADS) read_norm_kernel(const NormParams p) {
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(NORM_THREADS) read_norm_kernel(const NormParam
     const int64_t N = p.raw_off[r + 1] - p.raw_off[r];
     const double sc = p.scaling[r], of = p.offset[r];
     if (N <= 0 || !(sc > 0.0)) {     // empty read / non-physical scaling: numpy would give nan
-      if (tid == 0) { p.shift[r] = nan(""); p.scale[r] = nan(""); }
+      if (tid == 0) { p.shift[r] = nan(""); p.scale[r] = nan(""); p.vmin[r] = 0; p.bins[r] = 0; }
       continue;
     }
     // ---- min / max (vectorised 16-byte loads over the aligned body) ----
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(NORM_THREADS) read_norm_kernel(const NormParam
     lo = block_reduce<int>(lo, red_i, false, true);
     hi = block_reduce<int>(hi, red_i, true, false);
     const int bins = hi - lo + 1;
+    if (tid == 0) { p.vmin[r] = lo; p.bins[r] = bins; }
     uint32_t* hist = (bins <= SMEM_BINS) ? hist_s : p.gscratch + (size_t)blockIdx.x * 65536;
     for (int i = tid; i < bins; i += NORM_THREADS) hist[i] = 0;
     __syncthreads();
@@ -206,6 +209,21 @@ __global__ void __launch_bounds__(NORM_THREADS) read_norm_kernel(const NormParam
   }
 }
 
+// Normalisation is elementwise in the raw int16 value, so each read gets a float64 table
+//   lut[v - vmin] = around((scaling*(v+offset) - shift)/scale, 6)
+// (a few hundred to a few thousand entries) and every later kernel is a gather from it.
+__global__ void lut_kernel(const int64_t* __restrict__ lut_off, const int32_t* __restrict__ vmin, const double* __restrict__ scaling,
+                           const double* __restrict__ offset, const double* __restrict__ shift, const double* __restrict__ scale,
+                           int64_t R, int64_t total_bins, double* __restrict__ lut) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_bins) return;
+  int64_t a = 0, b = R;        // largest r with lut_off[r] <= i
+  while (b - a > 1) { const int64_t m = (a + b) >> 1; if (lut_off[m] <= i) a = m; else b = m; }
+  const int r = (int)a;
+  const int v = vmin[r] + (int)(i - lut_off[r]);
+  lut[i] = normalise(rescale(scaling[r], offset[r], v), shift[r], scale[r]);
+}
+
 // numpy's pairwise summation (DOUBLE_pairwise_sum): < 8 sequential, <= 128 eight-way unrolled, else halves.
 template <class F> __device__ double pairwise_block(const F& f, int a0, int n) {
   if (n < 8) {
@@ -254,15 +272,15 @@ __device__ __forceinline__ int find_read(const int64_t* off, int64_t R, int64_t 
 }
 
 struct BaseParams {
-  const int16_t* raw; const int64_t* raw_off; const double* scaling; const double* offset;
+  const int16_t* raw; const int64_t* raw_off;
   const int32_t* ev_start; const int32_t* ev_len; const int64_t* ev_off; int64_t R; int64_t total_ev;
-  const double* shift; const double* scale;
+  const double* lut; const int64_t* lut_off; const int32_t* vmin;
   double* base_mean; double* base_std; int32_t* base_len;
 };
 
 struct NormAt {
-  const int16_t* x; double sc, of, shift, scale;
-  __device__ double operator()(int i) const { return normalise(rescale(sc, of, x[i]), shift, scale); }
+  const int16_t* x; const double* lut;       // lut already offset by -vmin
+  __device__ double operator()(int i) const { return __ldg(lut + x[i]); }
 };
 struct SqDevAt {
   NormAt f; double mean;
@@ -282,7 +300,7 @@ __global__ void base_stats_kernel(const BaseParams p) {
   const int n = (int)(e0 - s0);
   p.base_len[e] = n;
   if (n == 0) { p.base_mean[e] = nan(""); p.base_std[e] = nan(""); return; }   // np.mean([]) -> nan
-  NormAt f{p.raw + p.raw_off[r] + s0, p.scaling[r], p.offset[r], p.shift[r], p.scale[r]};
+  NormAt f{p.raw + p.raw_off[r] + s0, p.lut + p.lut_off[r] - p.vmin[r]};
   const double mean = __ddiv_rn(pairwise_sum(f, 0, n), (double)n);
   SqDevAt g{f, mean};
   const double var = __ddiv_rn(pairwise_sum(g, 0, n), (double)n);
@@ -387,7 +405,7 @@ __global__ void __launch_bounds__(128) site_emit_kernel(const uint8_t* ev_base, 
 
 struct SiteParams {
   dsb_reads rd;
-  const double* shift; const double* scale;
+  const double* lut; const int64_t* lut_off; const int32_t* vmin;
   const double* base_mean; const double* base_std; const int32_t* base_len;
   const int32_t* site_read_in; const int32_t* site_loc_in;
   dsb_sites out;
@@ -466,7 +484,7 @@ __global__ void __launch_bounds__(SITE_WARPS * 32) site_feature_kernel(const Sit
   if (lane == 0 && p.out.window) {
     p.out.window[site * 3] = mode; p.out.window[site * 3 + 1] = start; p.out.window[site * 3 + 2] = nreal;
   }
-  const double sc = p.rd.scaling[r], of = p.rd.offset[r], sh = p.shift[r], sl = p.scale[r];
+  const double* lut = p.lut + p.lut_off[r] - p.vmin[r];
   for (int j = lane; j < S; j += 32) {
     double v = 0.0;
     if (j < nreal) {
@@ -474,7 +492,7 @@ __global__ void __launch_bounds__(SITE_WARPS * 32) site_feature_kernel(const Sit
       const int q = (mode == 1) ? start + (int)(((int64_t)j * midlen) / S) : start + j;
       int b = 0;
       while (b + 1 < K && cum[b + 1] <= q) ++b;
-      v = normalise(rescale(sc, of, x[st[b] + (q - cum[b])]), sh, sl);
+      v = __ldg(lut + x[st[b] + (q - cum[b])]);
     }
     if (p.out.signals) p.out.signals[site * S + j] = (float)v;
     if (p.out.signals64) p.out.signals64[site * S + j] = v;
@@ -513,20 +531,14 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
   w.base_len.ensure(std::max<int64_t>(total_ev, 1) * sizeof(int32_t));
   w.counts.ensure(R * sizeof(int64_t));
   w.offsets.ensure((R + 1) * sizeof(int64_t));
-  w.total.ensure(sizeof(int64_t));
 
+  w.vmin.ensure(R * sizeof(int32_t));
+  w.bins.ensure(R * sizeof(int64_t));
+  w.lut_off.ensure((R + 1) * sizeof(int64_t));
   NormParams np{rd->raw, rd->raw_off, rd->scaling, rd->offset, R, prm->normalize_method,
-                w.shift.as<double>(), w.scale.as<double>(), w.scratch.as<uint32_t>()};
+                w.shift.as<double>(), w.scale.as<double>(), w.scratch.as<uint32_t>(), w.vmin.as<int32_t>(), w.bins.as<int64_t>()};
   read_norm_kernel<<<grid_norm, NORM_THREADS, 0, s>>>(np);
   DSB_CUDA(cudaGetLastError());
-  ctx->launches++;
-  if (total_ev > 0) {
-    BaseParams bp{rd->raw, rd->raw_off, rd->scaling, rd->offset, rd->ev_start, rd->ev_len, rd->ev_off, R, total_ev,
-                  w.shift.as<double>(), w.scale.as<double>(), w.base_mean.as<double>(), w.base_std.as<double>(), w.base_len.as<int32_t>()};
-    base_stats_kernel<<<(unsigned)((total_ev + 127) / 128), 128, 0, s>>>(bp);
-    DSB_CUDA(cudaGetLastError());
-    ctx->launches++;
-  }
   MotifSet ms;
   memset(&ms, 0, sizeof ms);
   ms.n = prm->n_motifs; ms.len = prm->motif_len; ms.mod_loc = prm->mod_loc; ms.nbh = (prm->kmer_len - 1) / 2;
@@ -534,13 +546,31 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
   const int grid_r = (int)std::min<int64_t>(R, (int64_t)ctx->sm_count * 16);
   site_count_kernel<<<grid_r, 128, 0, s>>>(rd->ev_base, rd->ev_off, R, ms, w.counts.as<int64_t>());
   DSB_CUDA(cudaGetLastError());
+  w.total.ensure(2 * sizeof(int64_t));
   scan_kernel<<<1, 1024, 0, s>>>(w.counts.as<int64_t>(), w.offsets.as<int64_t>(), R, w.total.as<int64_t>());
+  scan_kernel<<<1, 1024, 0, s>>>(w.bins.as<int64_t>(), w.lut_off.as<int64_t>(), R, w.total.as<int64_t>() + 1);
   DSB_CUDA(cudaGetLastError());
-  ctx->launches += 2;
-  int64_t total = 0;
-  DSB_CUDA(cudaMemcpyAsync(&total, w.total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  ctx->launches += 4;
+  int64_t totals[2] = {0, 0};
+  DSB_CUDA(cudaMemcpyAsync(totals, w.total.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   DSB_CUDA(cudaStreamSynchronize(s));
+  const int64_t total = totals[0], total_bins = totals[1];
   *n_sites = total;
+  w.lut.ensure(std::max<int64_t>(total_bins, 1) * sizeof(double));
+  if (total_bins > 0) {
+    lut_kernel<<<(unsigned)((total_bins + 255) / 256), 256, 0, s>>>(w.lut_off.as<int64_t>(), w.vmin.as<int32_t>(), rd->scaling, rd->offset,
+                                                                    w.shift.as<double>(), w.scale.as<double>(), R, total_bins, w.lut.as<double>());
+    DSB_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (total_ev > 0) {
+    BaseParams bp{rd->raw, rd->raw_off, rd->ev_start, rd->ev_len, rd->ev_off, R, total_ev,
+                  w.lut.as<double>(), w.lut_off.as<int64_t>(), w.vmin.as<int32_t>(),
+                  w.base_mean.as<double>(), w.base_std.as<double>(), w.base_len.as<int32_t>()};
+    base_stats_kernel<<<(unsigned)((total_ev + 127) / 128), 128, 0, s>>>(bp);
+    DSB_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
   const int64_t emit = std::min<int64_t>(total, sites->capacity);
   if (read_shift) DSB_CUDA(cudaMemcpyAsync(read_shift, w.shift.p, R * sizeof(double), cudaMemcpyDeviceToDevice, s));
   if (read_scale) DSB_CUDA(cudaMemcpyAsync(read_scale, w.scale.p, R * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -558,7 +588,7 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
     DSB_CUDA(cudaGetLastError());
     SiteParams sp;
     sp.rd = *rd;
-    sp.shift = w.shift.as<double>(); sp.scale = w.scale.as<double>();
+    sp.lut = w.lut.as<double>(); sp.lut_off = w.lut_off.as<int64_t>(); sp.vmin = w.vmin.as<int32_t>();
     sp.base_mean = w.base_mean.as<double>(); sp.base_std = w.base_std.as<double>(); sp.base_len = w.base_len.as<int32_t>();
     sp.site_read_in = sr; sp.site_loc_in = sl;
     sp.out = *sites;

@@ -228,9 +228,43 @@ class Engine(object):
                                                   C.c_void_p(site_bufs["pred"].data_ptr()), C.c_void_p(stream)))
         return int(n_sites.value), site_bufs
 
+    def reads_to_device(self, reads, dev):
+        """Upload a :class:`ReadBatch` as the torch tensors ``dsb_extract_dev`` / ``dsb_extract_call_dev`` take."""
+        import torch
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+        return dict(raw=t(reads.raw, np.int16), raw_off=t(reads.raw_off, np.int64), scaling=t(reads.scaling, np.float64),
+                    offset=t(reads.offset, np.float64), ev_start=t(reads.ev_start, np.int32), ev_len=t(reads.ev_len, np.int32),
+                    ev_base=t(reads.ev_base, np.uint8), ev_off=t(reads.ev_off, np.int64),
+                    chrom_start=t(reads.chrom_start, np.int64), strand_minus=t(reads.strand_minus, np.uint8),
+                    chrom_len=t(reads.chrom_len, np.int64))
+
+    def extract_torch(self, dev_reads: dict, n_reads: int, site_bufs: dict, motif_seqs=("CG",), mod_loc=0,
+                      kmer_len=17, signal_len=360, normalize_method="mad"):
+        """Device-resident extraction (``dsb_extract_dev`` on torch's current stream) into ``site_bufs``
+        (from :meth:`alloc_site_bufs`); returns the number of sites."""
+        import torch
+        rd = _lib.Reads()
+        rd.n_reads = int(n_reads)
+        for k in ("raw", "raw_off", "scaling", "offset", "ev_start", "ev_len", "ev_base", "ev_off", "chrom_start",
+                  "strand_minus", "chrom_len"):
+            t = dev_reads.get(k)
+            setattr(rd, k, t.data_ptr() if t is not None else None)
+        mb, nm, ml = self._motif_bytes(motif_seqs)
+        prm = _lib.ExtractParams(int(kmer_len), int(signal_len), {"mad": 0, "zscore": 1}[normalize_method],
+                                 int(mod_loc), nm, ml, mb)
+        st = _lib.Sites()
+        st.capacity = site_bufs["capacity"]
+        for f in _lib.SITE_FIELDS:
+            setattr(st, f, site_bufs[f].data_ptr() if f in site_bufs else None)
+        n_sites = C.c_int64(0)
+        stream = torch.cuda.current_stream(dev_reads["raw"].device).cuda_stream
+        self._check(self.lib.dsb_extract_dev(self.h, C.byref(rd), C.byref(prm), C.byref(st), C.byref(n_sites),
+                                             None, None, C.c_void_p(stream)))
+        return int(n_sites.value)
+
     def alloc_site_bufs(self, capacity: int, dev):
         import torch
-        K, S = self.kmer_len, self.signal_len
+        K, S = self.kmer_len or 17, self.signal_len or 360
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
         return dict(capacity=int(capacity), site_read=mk((capacity,), torch.int32), site_loc=mk((capacity,), torch.int32),
                     pos=mk((capacity,), torch.int64), pos_in_strand=mk((capacity,), torch.int64),
