@@ -231,7 +231,7 @@ def main():
         sample = "{} samples per step, torch-CPU fp32 restatement of the un-folded graph, batch 512".format(per_step)
         print(json.dumps({
             "impl": "reference", "metric": "CpG samples/sec (call_mods forward)", "value": val, "unit": "samples/s",
-            "n_gpus": 0, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / a.steps,
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "samples_per_step": per_step},
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
