@@ -276,10 +276,10 @@ struct Builder {
             sb.flops_per_row = 2.0 * (96.0 * 48 + 160.0 * 48 + 96.0 * 64 + 64.0 * 48) * (double)L / (double)Lp;
             if (place) {
               std::vector<float> ha(240), hb(208);
-              for (int k = 0; k < 192; ++k) ha[k] = fb.p1.bias[k];
-              for (int k = 0; k < 48; ++k) ha[192 + k] = fb.b1.bias[k];
-              for (int k = 0; k < 48; ++k) { hb[k] = fb.b3.bias[k]; hb[48 + k] = fb.b4.bias[k]; hb[160 + k] = fb.b5c.bias[k]; }
-              for (int k = 0; k < 64; ++k) hb[96 + k] = fb.b5b.bias[k];
+              for (int k = 0; k < 48; ++k) ha[k] = fb.b1.bias[k];          // accumulator order: b1 | p1
+              for (int k = 0; k < 192; ++k) ha[48 + k] = fb.p1.bias[k];
+              for (int k = 0; k < 48; ++k) { hb[k] = fb.b3.bias[k]; hb[48 + k] = fb.b4.bias[k]; hb[96 + k] = fb.b5c.bias[k]; }
+              for (int k = 0; k < 64; ++k) hb[144 + k] = fb.b5b.bias[k];     // b3 | b4 | b5c | b5b
               DSB_CUDA(cudaMemcpyAsync(biasA, ha.data(), 240 * sizeof(float), cudaMemcpyHostToDevice, up_stream));
               DSB_CUDA(cudaMemcpyAsync(biasB, hb.data(), 208 * sizeof(float), cudaMemcpyHostToDevice, up_stream));
               DSB_CUDA(cudaStreamSynchronize(up_stream));

@@ -1,6 +1,8 @@
 // incept_tc.cu — the two fused inception-block kernels (see incept_tc.cuh).  Both are persistent,
 // warp-specialised tcgen05 kernels with every conv weight of their half of the block resident in shared
 // memory, a TMA-fed ring of activation tiles, and double-buffered accumulators in TMEM.
+#include <cstdlib>
+
 #include "incept_tc.cuh"
 #include "tc_common.cuh"
 
@@ -44,22 +46,48 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Warp-cooperative store of a [32 rows x NP*8 columns] 16-bit block that the warp holds one row per lane
+// (TMEM layout).  The block is staged through a warp-private 2 KB shared-memory tile (64-byte rows, 16-byte
+// pieces XOR-swizzled by (row >> 1) & 3 so both the row-wise writes and the piece-wise reads are conflict free) and
+// written back with consecutive lanes on consecutive 16-byte pieces: every store instruction covers whole
+// 64-byte (NP = 4) row segments, 8 rows at a time, instead of 32 scattered 16-byte pieces.
+template <int NP>
+__device__ __forceinline__ void staged_store(uint32_t stage, const uint32_t (&pk)[16], int lane, uint32_t ok_mask,
+                                             uint8_t* dst_row0, size_t pitch_bytes) {
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+  for (int pc = 0; pc < NP; ++pc)
+    sts128(stage + (uint32_t)lane * 64u + (((uint32_t)pc ^ sw) << 4), make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const int id = j * 32 + lane;
+    const int ri = id / NP, pc = id % NP;
+    const uint4 v = lds128(stage + (uint32_t)ri * 64u + (((uint32_t)pc ^ (uint32_t)((ri >> 1) & 3)) << 4));
+    if ((ok_mask >> ri) & 1u) *reinterpret_cast<uint4*>(dst_row0 + (size_t)ri * pitch_bytes + pc * 16) = v;
+  }
+  __syncwarp();
+}
+
 // ============================================================================================
 // Kernel A
 // ============================================================================================
 constexpr int A_THREADS = 448;       // warp 0 TMA, warp 1 MMA, warps 2-5 pool, warps 6-13 epilogue
-constexpr int A_SLOTS = 6;
+constexpr int A_SLOTS = 5;
 constexpr uint32_t A_SLOT_BYTES = 128 * 64 * 2;        // one [128 x 64] SWIZZLE_128B tile
 constexpr uint32_t A_WP1_BLK = 192 * 64 * 2;           // 24576
 constexpr uint32_t A_WB1_BLK = 48 * 64 * 2;            // 6144
 constexpr int A_NKB = 4;
-constexpr uint32_t A_ACC_STRIDE = 256;                 // TMEM columns per accumulator stage (240 used)
+constexpr uint32_t A_ACC_STRIDE = 256;                 // TMEM columns per accumulator stage (240 used):
+                                                       // b1 [0,48) b2 [48,96) b3a [96,128) b4a [128,160) b5a [160,192) stem [192,240)
+constexpr uint32_t EPI_STAGE_BYTES = 32 * 64;          // per epilogue warp
 
 struct ASmem {
   static constexpr uint32_t wp1 = 0;
   static constexpr uint32_t wb1 = wp1 + A_NKB * A_WP1_BLK;
   static constexpr uint32_t ring = wb1 + A_NKB * A_WB1_BLK;
-  static constexpr uint32_t bars = ring + A_SLOTS * A_SLOT_BYTES;
+  static constexpr uint32_t stage = ring + A_SLOTS * A_SLOT_BYTES;          // 8 epilogue warps x 2 KB
+  static constexpr uint32_t bars = stage + 8 * EPI_STAGE_BYTES;
   // barriers: full_x[S] p1_done[S] full_xp[S] empty[S] wbar tfull[2] tempty[2]
   static constexpr uint32_t nbars = 4 * A_SLOTS + 5;
   static constexpr uint32_t tmem_slot = (bars + 8 * nbars + 15u) & ~15u;
@@ -132,7 +160,7 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_p1 = tmem_base + acc * A_ACC_STRIDE, d_b1 = d_p1 + 192;
+        const uint32_t d_b1 = tmem_base + acc * A_ACC_STRIDE, d_p1 = d_b1 + 48;
         // software-pipelined issue order p1(0) p1(1) b1(0) p1(2) b1(1) p1(3) b1(2) b1(3): a slot is released one
         // step after its p1 MMAs, so the TMA ring keeps most of its slots in flight.
         int sp = slot, sb = slot;
@@ -181,6 +209,7 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
       for (int j = 0; j < A_NKB; ++j) {
         const uint32_t tb = base + ASmem::ring + slot * A_SLOT_BYTES;
         mbar_wait(full_x(slot), phase);
+        if (p.ablate & 1) { mbar_wait(p1_done(slot), phase); __syncwarp(); if (lane == 0) mbar_arrive(full_xp(slot)); if (++slot == A_SLOTS) { slot = 0; phase ^= 1u; } continue; }
         uint4 in[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
@@ -214,24 +243,29 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
     // ---------------- epilogue warps ----------------
     const int q = warp & 3;
     const int half = (warp - 6) >> 2;
+    const uint32_t stage = base + ASmem::stage + (uint32_t)(warp - 6) * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int i = q * 32 + lane;                       // tile row
       const int row = tile * INCEPT_A_TILE_ROWS - 1 + i;
+      const int wrow0 = tile * INCEPT_A_TILE_ROWS - 1 + q * 32;   // global row of this warp's lane 0
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * A_ACC_STRIDE;
-      const bool row_ok = i >= 1 && i <= INCEPT_A_TILE_ROWS && row < p.M;
+      const bool row_ok = i >= 1 && i <= INCEPT_A_TILE_ROWS && row < p.M && !(p.ablate & 2);
+      const uint32_t ok_mask = __ballot_sync(0xffffffffu, row_ok);
       const bool halo = (row % p.Lp) >= p.L;
-      for (int c = half * 32; c < 240; c += 64) {
-        const bool two = c + 32 <= 240;
+      // 32-column groups: g0..g2 -> Y[:, 0:96) (b1 | b2), g3/g4/g5 -> planes P3/P4/P5, g6 + g7 (16 wide) -> stem plane
+      for (int g = half; g < 8; g += 2) {
+        const int c = g * 32;
+        const bool two = g < 7;
         uint32_t rr[2][16];
         __syncwarp();
         tc_ld16(t_row + (uint32_t)c, rr[0]);
         if (two) tc_ld16(t_row + (uint32_t)(c + 16), rr[1]);
         tc_wait_ld();
-        if (!row_ok) continue;
+        uint32_t pk[16];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           if (h2 == 1 && !two) break;
@@ -245,8 +279,7 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
             v[4 * k + 2] = __uint_as_float(rr[h2][4 * k + 2]) + bb.z;
             v[4 * k + 3] = __uint_as_float(rr[h2][4 * k + 3]) + bb.w;
           }
-          const bool relu = !(col >= 144 && col < 192);  // the residual stem keeps its sign
-          if (relu) {
+          if (g < 6) {                                    // the residual stem (g6, g7) keeps its sign
 #pragma unroll
             for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
           }
@@ -254,17 +287,16 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
 #pragma unroll
             for (int k = 0; k < 16; ++k) v[k] = 0.f;
           }
-          uint16_t* dst;
-          if (col < 48) dst = reinterpret_cast<uint16_t*>(p.Y) + (size_t)row * p.ldY + 48 + col;            // b2
-          else if (col < 80) dst = reinterpret_cast<uint16_t*>(p.P3) + (size_t)row * 32 + (col - 48);       // b3a
-          else if (col < 112) dst = reinterpret_cast<uint16_t*>(p.P4) + (size_t)row * 32 + (col - 80);      // b4a
-          else if (col < 144) dst = reinterpret_cast<uint16_t*>(p.P5) + (size_t)row * 32 + (col - 112);     // b5a
-          else if (col < 192) dst = reinterpret_cast<uint16_t*>(p.PS) + (size_t)row * 48 + (col - 144);     // stem
-          else dst = reinterpret_cast<uint16_t*>(p.Y) + (size_t)row * p.ldY + (col - 192);                  // b1
-          uint4* dp = reinterpret_cast<uint4*>(dst);
-          dp[0] = make_uint4(pack16<F16>(v[0], v[1]), pack16<F16>(v[2], v[3]), pack16<F16>(v[4], v[5]), pack16<F16>(v[6], v[7]));
-          dp[1] = make_uint4(pack16<F16>(v[8], v[9]), pack16<F16>(v[10], v[11]), pack16<F16>(v[12], v[13]), pack16<F16>(v[14], v[15]));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pk[8 * h2 + k] = pack16<F16>(v[2 * k], v[2 * k + 1]);
         }
+        uint8_t* dst;
+        size_t pitch;
+        if (g < 3) { pitch = (size_t)p.ldY * 2; dst = reinterpret_cast<uint8_t*>(p.Y) + (ptrdiff_t)wrow0 * (ptrdiff_t)pitch + g * 64; }
+        else if (g < 6) { pitch = 64; dst = reinterpret_cast<uint8_t*>(g == 3 ? p.P3 : g == 4 ? p.P4 : p.P5) + (ptrdiff_t)wrow0 * 64; }
+        else { pitch = 96; dst = reinterpret_cast<uint8_t*>(p.PS) + (ptrdiff_t)wrow0 * 96 + (g - 6) * 64; }
+        if (two) staged_store<4>(stage, pk, lane, ok_mask, dst, pitch);
+        else staged_store<2>(stage, pk, lane, ok_mask, dst, pitch);
       }
       tc_fence_before();
       __syncwarp();
@@ -286,11 +318,12 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
 // Kernel B
 // ============================================================================================
 constexpr int B_THREADS = 448;       // warp 0 TMA, warp 1 MMA, warps 2-5 branch-5 staging, warps 6-13 epilogue
-constexpr int B_SLOTS = 16;
+constexpr int B_SLOTS = 14;
 constexpr uint32_t B_SLOT_BYTES = 128 * 32 * 2;        // one [128 x 32] SWIZZLE_64B tile
 constexpr uint32_t B_W48_BLK = 48 * 32 * 2;            // 3072
 constexpr uint32_t B_W64_BLK = 64 * 32 * 2;            // 4096
-constexpr uint32_t B_ACC_STRIDE = 256;                 // columns: b3 [0,48) b4 [48,96) b5b [96,160) b5c [160,208)
+constexpr uint32_t B_ACC_STRIDE = 160;                 // columns: b3 [0,48) b4 [48,96) b5b [96,160), b5c re-uses [96,144)
+constexpr int B_ACC_STAGES = 3;
 constexpr int B_LOADS = 11;                            // b5b x3, b3 x3, b4 x5
 
 struct BSmem {
@@ -298,11 +331,12 @@ struct BSmem {
   static constexpr uint32_t w4 = w3 + 3 * B_W48_BLK;
   static constexpr uint32_t w5b = w4 + 5 * B_W48_BLK;
   static constexpr uint32_t w5c = w5b + 3 * B_W64_BLK;
-  static constexpr uint32_t u = w5c + 2 * B_W48_BLK;          // 43008: 2 stages x two [128 x 32] blocks
-  static constexpr uint32_t ring = u + 4 * B_SLOT_BYTES;
-  static constexpr uint32_t bars = ring + B_SLOTS * B_SLOT_BYTES;
-  // barriers: full[S] empty[S] wbar b5b_full[2] u_full[2] tfull[2] tempty[2]
-  static constexpr uint32_t nbars = 2 * B_SLOTS + 9;
+  static constexpr uint32_t u = w5c + 2 * B_W48_BLK;          // 43008: 3 stages x two [128 x 32] blocks
+  static constexpr uint32_t ring = u + 2 * B_ACC_STAGES * B_SLOT_BYTES;
+  static constexpr uint32_t stage = ring + B_SLOTS * B_SLOT_BYTES;          // 8 epilogue warps x 2 KB
+  static constexpr uint32_t bars = stage + 8 * EPI_STAGE_BYTES;
+  // barriers: full[S] empty[S] wbar b5b_full[3] u_full[3] tfull[3] tempty[3]
+  static constexpr uint32_t nbars = 2 * B_SLOTS + 1 + 4 * B_ACC_STAGES;
   static constexpr uint32_t tmem_slot = (bars + 8 * nbars + 15u) & ~15u;
   static constexpr uint32_t bias = tmem_slot + 16;
   static constexpr uint32_t total = bias + 208 * 4;
@@ -318,16 +352,16 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
   auto empty = [&](int s) { return base + BSmem::bars + 8u * (B_SLOTS + s); };
   const uint32_t wbar = base + BSmem::bars + 8u * (2 * B_SLOTS);
   auto b5b_full = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + a); };
-  auto u_full = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 3 + a); };
-  auto tfull = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 5 + a); };
-  auto tempty = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 7 + a); };
+  auto u_full = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + B_ACC_STAGES + a); };
+  auto tfull = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + 2 * B_ACC_STAGES + a); };
+  auto tempty = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + 3 * B_ACC_STAGES + a); };
   const uint32_t tmem_slot = base + BSmem::tmem_slot;
   float* sbias = reinterpret_cast<float*>(smem_raw + (base + BSmem::bias - smem_u32(smem_raw)));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < B_SLOTS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     mbar_init(wbar, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(b5b_full(a), 1); mbar_init(u_full(a), 4); mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
+    for (int a = 0; a < B_ACC_STAGES; ++a) { mbar_init(b5b_full(a), 1); mbar_init(u_full(a), 4); mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 208; i += B_THREADS) sbias[i] = p.bias[i];
@@ -374,39 +408,51 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
     if (lane == 0 && (int)blockIdx.x < num_tiles) {
       const uint32_t id48 = idesc_f16(F16, 48), id64 = idesc_f16(F16, 64);
       mbar_wait(wbar, 0);
-      int slot = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty(acc), acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * B_ACC_STRIDE;
-        auto run = [&](int ntaps, uint32_t w_off, uint32_t w_blk, uint32_t d, uint32_t idesc) {
-          for (int t = 0; t < ntaps; ++t) {
-            mbar_wait(full(slot), phase);
-            tc_fence_after();
-            const uint64_t ad = make_kmajor_desc<32>(base + BSmem::ring + slot * B_SLOT_BYTES);
-            const uint64_t bd = make_kmajor_desc<32>(base + w_off + t * w_blk);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto run = [&](int ntaps, uint32_t w_off, uint32_t w_blk, uint32_t d, uint32_t idesc) {
+        for (int t = 0; t < ntaps; ++t) {
+          mbar_wait(full(slot), phase);
+          tc_fence_after();
+          const uint64_t ad = make_kmajor_desc<32>(base + BSmem::ring + slot * B_SLOT_BYTES);
+          const uint64_t bd = make_kmajor_desc<32>(base + w_off + t * w_blk);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) tc_mma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (t | k) != 0 ? 1u : 0u);
-            tc_commit(empty(slot));
-            if (++slot == B_SLOTS) { slot = 0; phase ^= 1u; }
-          }
-        };
+          for (int k = 0; k < 2; ++k) tc_mma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (t | k) != 0 ? 1u : 0u);
+          tc_commit(empty(slot));
+          if (++slot == B_SLOTS) { slot = 0; phase ^= 1u; }
+        }
+      };
+      // tap GEMMs of one tile into accumulator stage `a`: branch 5 first so its staging starts early
+      auto front = [&](int a, uint32_t a_phase) {
+        mbar_wait(tempty(a), a_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + a * B_ACC_STRIDE;
         run(3, BSmem::w5b, B_W64_BLK, d0 + 96, id64);
-        tc_commit(b5b_full(acc));
+        tc_commit(b5b_full(a));
         run(3, BSmem::w3, B_W48_BLK, d0, id48);
         run(5, BSmem::w4, B_W48_BLK, d0 + 48, id48);
+      };
+      // software pipeline across tiles: the tap GEMMs of tile i+1 are issued before waiting for the staged
+      // relu(b5b) tile of tile i, so the TMEM -> smem round trip of branch 5 is off the critical path.
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      if ((int)blockIdx.x < num_tiles) front(0, 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nacc = (acc + 1 == B_ACC_STAGES) ? 0 : acc + 1;
+        const uint32_t nphase = (nacc == 0) ? (acc_phase ^ 1u) : acc_phase;
+        if (tile + (int)gridDim.x < num_tiles) front(nacc, nphase);
+        const uint32_t d0 = tmem_base + acc * B_ACC_STRIDE;
         mbar_wait(u_full(acc), acc_phase);                // relu(b5b) tile of this stage is in shared memory
         tc_fence_after();
         for (int kb = 0; kb < 2; ++kb) {
           const uint64_t ad = make_kmajor_desc<32>(base + BSmem::u + (2 * acc + kb) * B_SLOT_BYTES);
           const uint64_t bd = make_kmajor_desc<32>(base + BSmem::w5c + kb * B_W48_BLK);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) tc_mma_bf16(d0 + 160, ad + 2 * k, bd + 2 * k, id48, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 2; ++k) tc_mma_bf16(d0 + 96, ad + 2 * k, bd + 2 * k, id48, (kb | k) != 0 ? 1u : 0u);
         }
         tc_commit(tfull(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        acc = nacc;
+        acc_phase = nphase;
       }
     }
   } else if (warp < 6) {
@@ -434,8 +480,8 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[4];
           const int e0 = kb * 32 + c * 8;                      // first b5b output channel of this 16-byte chunk
-          const float4 b0 = *reinterpret_cast<const float4*>(sbias + 96 + e0);
-          const float4 b1 = *reinterpret_cast<const float4*>(sbias + 96 + e0 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(sbias + 144 + e0);
+          const float4 b1 = *reinterpret_cast<const float4*>(sbias + 144 + e0 + 4);
           const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -452,75 +498,83 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(u_full(acc));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == B_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ---------------- epilogue warps: b3, b4, b5 = relu(stem + b5c) -> Y[:, 96:240] ----------------
+    // accumulator column t (b3 [0,48) | b4 [48,96) | b5c [96,144)) is output channel 96 + t and bias index t.
     const int q = warp & 3;
     const int half = (warp - 6) >> 2;
+    const uint32_t stage = base + BSmem::stage + (uint32_t)(warp - 6) * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int i = q * 32 + lane;
       const int row = tile * 128 + i;
-      const bool row_ok = row < p.M;
+      const int wrow0 = tile * 128 + q * 32;
+      const bool row_ok = row < p.M && !(p.ablate & 2);
+      const uint32_t ok_mask = __ballot_sync(0xffffffffu, row_ok);
       const bool halo = (row % p.Lp) >= p.L;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * B_ACC_STRIDE;
-      // the residual (stem plane) is an input: fetch it before waiting for the accumulators
-      uint4 res[2][2];
+      // the residual (stem plane) is an input: fetch it before waiting for the accumulators.
+      // warp set 1 owns group 3 (stem channels 0..31), warp set 0 owns group 4 (stem channels 32..47).
+      uint4 res[4];
       {
-        const uint16_t* tp = reinterpret_cast<const uint16_t*>(p.PS) + (size_t)(row_ok ? row : 0) * 48;
-        const int s0 = half == 0 ? 0 : 1, s1 = 2;             // grp-2 sub-chunks of this warp set: {0, 2} or {1}
-        res[0][0] = __ldg(reinterpret_cast<const uint4*>(tp + s0 * 16));
-        res[0][1] = __ldg(reinterpret_cast<const uint4*>(tp + s0 * 16) + 1);
-        res[1][0] = __ldg(reinterpret_cast<const uint4*>(tp + s1 * 16));
-        res[1][1] = __ldg(reinterpret_cast<const uint4*>(tp + s1 * 16) + 1);
+        const uint4* tp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.PS) + (size_t)(row < p.M ? row : 0) * 48);
+        if (half == 1) { res[0] = __ldg(tp); res[1] = __ldg(tp + 1); res[2] = __ldg(tp + 2); res[3] = __ldg(tp + 3); }
+        else { res[0] = __ldg(tp + 4); res[1] = __ldg(tp + 5); res[2] = res[0]; res[3] = res[1]; }
       }
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
-      for (int ch = half; ch < 9; ch += 2) {
-        const int grp = ch / 3, sub = ch % 3;                 // grp 0 b3, 1 b4, 2 b5c
-        const int tcol = (grp == 0 ? 0 : grp == 1 ? 48 : 160) + sub * 16;
-        const int ycol = 96 + grp * 48 + sub * 16;
-        uint32_t rr[16];
+      for (int g = half; g < 5; g += 2) {
+        const int t0 = g * 32;
+        const bool two = g < 4;
+        uint32_t rr[2][16];
         __syncwarp();
-        tc_ld16(t_row + (uint32_t)tcol, rr);
+        tc_ld16(t_row + (uint32_t)t0, rr[0]);
+        if (two) tc_ld16(t_row + (uint32_t)(t0 + 16), rr[1]);
         tc_wait_ld();
-        if (!row_ok) continue;
-        float v[16];
+        uint32_t pk[16];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float4 bb = *reinterpret_cast<const float4*>(sbias + tcol + 4 * k);
-          v[4 * k + 0] = __uint_as_float(rr[4 * k + 0]) + bb.x;
-          v[4 * k + 1] = __uint_as_float(rr[4 * k + 1]) + bb.y;
-          v[4 * k + 2] = __uint_as_float(rr[4 * k + 2]) + bb.z;
-          v[4 * k + 3] = __uint_as_float(rr[4 * k + 3]) + bb.w;
-        }
-        if (grp == 2) {
+        for (int h2 = 0; h2 < 2; ++h2) {
+          if (h2 == 1 && !two) break;
+          const int t = t0 + 16 * h2;
+          float v[16];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint4 rv = (sub == 2) ? res[1][h] : res[0][h];
-            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+          for (int k = 0; k < 4; ++k) {
+            const float4 bb = *reinterpret_cast<const float4*>(sbias + t + 4 * k);
+            v[4 * k + 0] = __uint_as_float(rr[h2][4 * k + 0]) + bb.x;
+            v[4 * k + 1] = __uint_as_float(rr[h2][4 * k + 1]) + bb.y;
+            v[4 * k + 2] = __uint_as_float(rr[h2][4 * k + 2]) + bb.z;
+            v[4 * k + 3] = __uint_as_float(rr[h2][4 * k + 3]) + bb.w;
+          }
+          if (g >= 3) {                                   // + stem
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 f = unpack16<F16>(w[k]);
-              v[8 * h + 2 * k] += f.x;
-              v[8 * h + 2 * k + 1] += f.y;
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint4 rv = res[2 * h2 + hh];
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack16<F16>(w[k]);
+                v[8 * hh + 2 * k] += f.x;
+                v[8 * hh + 2 * k + 1] += f.y;
+              }
             }
           }
-        }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = halo ? 0.f : fmaxf(v[k], 0.f);
-        uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.Y) + (size_t)row * p.ldY + ycol);
-        dp[0] = make_uint4(pack16<F16>(v[0], v[1]), pack16<F16>(v[2], v[3]), pack16<F16>(v[4], v[5]), pack16<F16>(v[6], v[7]));
-        dp[1] = make_uint4(pack16<F16>(v[8], v[9]), pack16<F16>(v[10], v[11]), pack16<F16>(v[12], v[13]), pack16<F16>(v[14], v[15]));
+          for (int k = 0; k < 16; ++k) v[k] = halo ? 0.f : fmaxf(v[k], 0.f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pk[8 * h2 + k] = pack16<F16>(v[2 * k], v[2 * k + 1]);
+        }
+        const size_t pitch = (size_t)p.ldY * 2;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(p.Y) + (ptrdiff_t)wrow0 * (ptrdiff_t)pitch + (96 + t0) * 2;
+        if (two) staged_store<4>(stage, pk, lane, ok_mask, dst, pitch);
+        else staged_store<2>(stage, pk, lane, ok_mask, dst, pitch);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(acc));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == B_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
@@ -549,6 +603,7 @@ void launch_incept_a(const InceptALaunch& L, int M, int sm_count, cudaStream_t s
   const int grid = num_tiles < sm_count ? num_tiles : sm_count;
   InceptAParams p = L.p;
   p.M = M;
+  if (const char* ev = getenv("DSB_ABLATE_A")) p.ablate = atoi(ev);
   const size_t smem = ASmem::total + 1024;
   static bool cfg[2][64] = {{false}};
   if (L.fp16) {
@@ -567,6 +622,7 @@ void launch_incept_b(const InceptBLaunch& L, int M, int sm_count, cudaStream_t s
   const int grid = num_tiles < sm_count ? num_tiles : sm_count;
   InceptBParams p = L.p;
   p.M = M;
+  if (const char* ev = getenv("DSB_ABLATE_B")) p.ablate = atoi(ev);
   const size_t smem = BSmem::total + 1024;
   static bool cfg[2][64] = {{false}};
   if (L.fp16) {

@@ -20,7 +20,8 @@ struct InceptAParams {
   void* Y = nullptr; int ldY = 0;
   void* P3 = nullptr; void* P4 = nullptr; void* P5 = nullptr;   // [M][32] planes: b3a, b4a, b5a
   void* PS = nullptr;                                           // [M][48] plane: residual stem
-  const float* bias = nullptr; // [240]: p1 (b2 48 | b3a 32 | b4a 32 | b5a 32 | stem 48) then b1 (48)
+  int ablate = 0;              // timing experiments only (DSB_ABLATE_A): 1 skip pool math, 2 skip epilogue stores
+  const float* bias = nullptr; // [240]: b1 (48) then p1 (b2 48 | b3a 32 | b4a 32 | b5a 32 | stem 48)
 };
 struct InceptALaunch { InceptAMaps maps; InceptAParams p; bool fp16 = false; };
 
@@ -29,7 +30,8 @@ struct InceptBParams {
   int M = 0, Lp = 0, L = 0;
   const void* PS = nullptr;    // [M][48] residual stem plane
   void* Y = nullptr; int ldY = 0;
-  const float* bias = nullptr; // [208]: b3 48 | b4 48 | b5b 64 | b5c 48
+  int ablate = 0;              // timing experiments only (DSB_ABLATE_B): 1 skip staging math, 2 skip epilogue stores
+  const float* bias = nullptr; // [208]: b3 48 | b4 48 | b5c 48 | b5b 64
 };
 struct InceptBLaunch { InceptBMaps maps; InceptBParams p; bool fp16 = false; };
 
