@@ -567,7 +567,8 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
         break;
       }
       case ST_ZERO:
-        DSB_CUDA(cudaMemsetAsync(st.dst, 0, st.zero_bytes_per_sample * (size_t)n, s));
+        // whole 128-row tiles: the tensor-core path keeps the cell state in a tile-interleaved layout
+        DSB_CUDA(cudaMemsetAsync(st.dst, 0, st.zero_bytes_per_sample * (size_t)((n + 127) / 128 * 128), s));
         break;
       case ST_HEAD: {
         if (multi) {

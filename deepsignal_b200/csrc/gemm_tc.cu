@@ -10,6 +10,8 @@
 // Accumulators are double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  A-operand "segments" give k-tap convs (row-shifted TMA boxes; out-of-range rows are
 // zero-filled by TMA, sample edges read the zero halo rows) and [x_t | h_{t-1}] for the LSTM.
+#include <cstdlib>
+
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
 
@@ -23,7 +25,7 @@ constexpr int BM_TC = 128;
 
 template <int BK, int EPI, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const int m_tiles, const uint32_t tmem_cols) {
+gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const int m_tiles, const uint32_t tmem_cols, const int ablate) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -44,6 +46,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
   const uint32_t bres_bar = bar_base + 8u * (2 * stages + 4);
   const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 6);
   float* sbias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));   // [N] floats
+  const uint32_t stage_base = (tmem_slot + 16u + (uint32_t)p.epi.N * 4u + 15u) & ~15u;           // 8 x 2 KB epilogue staging
   const int n_tiles_n = p.epi.N / BN;
   // tile walk: streaming mode interleaves (m, n) tiles over all CTAs; resident mode pins a CTA to one n tile
   const int my_n = resident ? (int)(blockIdx.x % n_tiles_n) : 0;
@@ -142,9 +145,15 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      const bool row_ok = row < e.M;
+      const bool row_ok = row < e.M && !(ablate & 2);
+      const uint32_t stage = stage_base + (uint32_t)(warp - 2) * EPI_STAGE_BYTES;
+      const uint32_t ok_mask = __ballot_sync(0xffffffffu, row_ok);
+      const int wrow0 = tile_m(tile) * BM_TC + q * 32;
       if constexpr (EPI == EPI_CONV) {
         const bool halo = e.Lp > 0 && (row % e.Lp) >= e.L;
+        // staging pays off for narrow row pitches (fused kernels' planes); for the 256/512-byte pitches of conv2/conv3 the
+        // direct 2 x 16-byte stores per lane measured faster, so the generic conv epilogue keeps them.
+        const bool staged = false;
         // 32-column groups; group g belongs to the warp set (g & 1) == half
         for (int c = half * 32; c < BN; c += 64) {
           const bool two = c + 32 <= BN;       // BN is a multiple of 16: the last group may hold 16 columns
@@ -153,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
           tc_ld16(t_row + (uint32_t)c, r[0]);
           if (two) tc_ld16(t_row + (uint32_t)(c + 16), r[1]);
           tc_wait_ld();
-          if (!row_ok) continue;
+          uint32_t pk[16];
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             if (h2 == 1 && !two) break;
@@ -168,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
               v[4 * i + 3] = __uint_as_float(r[h2][4 * i + 3]) + bb.w;
             }
             const bool first = col < e.split;
-            if (e.res != nullptr && first) {
+            if (e.res != nullptr && first && row_ok) {
               const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.res) + (size_t)row * e.res_ld + e.res_c0 + col);
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
@@ -190,30 +199,52 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = 0.f;
             }
-            uint16_t* dst = first ? reinterpret_cast<uint16_t*>(e.d0) + (size_t)row * e.ld0 + e.c0 + col
-                                  : reinterpret_cast<uint16_t*>(e.d1) + (size_t)row * e.ld1 + e.c1 + col - e.split;
-            uint4* dp = reinterpret_cast<uint4*>(dst);
-            dp[0] = make_uint4(pack16<F16>(v[0], v[1]), pack16<F16>(v[2], v[3]), pack16<F16>(v[4], v[5]), pack16<F16>(v[6], v[7]));
-            dp[1] = make_uint4(pack16<F16>(v[8], v[9]), pack16<F16>(v[10], v[11]), pack16<F16>(v[12], v[13]), pack16<F16>(v[14], v[15]));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[8 * h2 + i] = pack16<F16>(v[2 * i], v[2 * i + 1]);
+            if (!staged && row_ok) {
+              uint16_t* dst = first ? reinterpret_cast<uint16_t*>(e.d0) + (size_t)row * e.ld0 + e.c0 + col
+                                    : reinterpret_cast<uint16_t*>(e.d1) + (size_t)row * e.ld1 + e.c1 + col - e.split;
+              uint4* dp = reinterpret_cast<uint4*>(dst);
+              dp[0] = make_uint4(pk[8 * h2 + 0], pk[8 * h2 + 1], pk[8 * h2 + 2], pk[8 * h2 + 3]);
+              dp[1] = make_uint4(pk[8 * h2 + 4], pk[8 * h2 + 5], pk[8 * h2 + 6], pk[8 * h2 + 7]);
+            }
+          }
+          if (staged) {
+            const int col = n0 + c;
+            const bool first = col < e.split;
+            const size_t pitch = (size_t)(first ? e.ld0 : e.ld1) * 2;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(first ? e.d0 : e.d1) + (ptrdiff_t)wrow0 * (ptrdiff_t)pitch +
+                           (size_t)(first ? e.c0 + col : e.c1 + col - e.split) * 2;
+            if (two) staged_store<4>(stage, pk, lane, ok_mask, dst, pitch);
+            else staged_store<2>(stage, pk, lane, ok_mask, dst, pitch);
           }
         }
       } else {
         // LSTM: columns 4*u+g.  64 columns (16 hidden units) per iteration, iterations interleaved over the two warp sets.
+        // The cell state is private to this kernel, so it is kept in a thread-interleaved layout: block
+        // (m tile, 64-column iteration, lane quadrant) holds 4 float4 per lane, lane-minor -> every load/store
+        // instruction of a warp touches 512 contiguous bytes.
         for (int c = half * 64; c < BN; c += 128) {
           uint32_t r[4][16];
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) tc_ld16(t_row + (uint32_t)(c + 16 * i), r[i]);
-          tc_wait_ld();
-          if (!row_ok) continue;
           const int col = n0 + c;
           const int u0 = col >> 2;
-          float* cp = e.c + (size_t)row * HID + u0;
+          float4* cblk = reinterpret_cast<float4*>(e.c) + ((((size_t)tile_m(tile) * (GATES / 64) + (size_t)(col >> 6)) * 4 + q) * 4) * 32 + lane;
+          float4 cprev[4];
+          if (!(ablate & 2)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cprev[i] = cblk[i * 32];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cprev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          tc_wait_ld();
           float hn[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 cprev = *reinterpret_cast<const float4*>(cp + 4 * i);
-            const float cpv[4] = {cprev.x, cprev.y, cprev.z, cprev.w};
+            const float cpv[4] = {cprev[i].x, cprev[i].y, cprev[i].z, cprev[i].w};
             float cn[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -222,11 +253,13 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
                               __uint_as_float(r[i][4 * j + 2]) + b.z, __uint_as_float(r[i][4 * j + 3]) + b.w,
                               cpv[j], cn[j], hn[4 * i + j]);
             }
-            *reinterpret_cast<float4*>(cp + 4 * i) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            if (!(ablate & 2)) cblk[i * 32] = make_float4(cn[0], cn[1], cn[2], cn[3]);
           }
-          uint4* hp = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.h_out) + (size_t)row * HID + u0);
-          hp[0] = make_uint4(pack16<F16>(hn[0], hn[1]), pack16<F16>(hn[2], hn[3]), pack16<F16>(hn[4], hn[5]), pack16<F16>(hn[6], hn[7]));
-          hp[1] = make_uint4(pack16<F16>(hn[8], hn[9]), pack16<F16>(hn[10], hn[11]), pack16<F16>(hn[12], hn[13]), pack16<F16>(hn[14], hn[15]));
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = pack16<F16>(hn[2 * i], hn[2 * i + 1]);
+          uint8_t* hdst = reinterpret_cast<uint8_t*>(e.h_out) + ((ptrdiff_t)wrow0 * HID + u0) * 2;
+          staged_store<2>(stage, pk, lane, ok_mask, hdst, (size_t)HID * 2);
         }
       }
       tc_fence_before();
@@ -270,7 +303,8 @@ void launch_one(const TcLaunch& L, int m_tiles, int grid, uint32_t tmem_cols, cu
     DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[dev & 63] = true;
   }
-  launch_pdl(kern, grid, TC_THREADS, L.smem, s, L.maps, L.p, m_tiles, tmem_cols);
+  static const int ablate = getenv("DSB_ABLATE_G") ? atoi(getenv("DSB_ABLATE_G")) : 0;   // timing experiments only
+  launch_pdl(kern, grid, TC_THREADS, L.smem, s, L.maps, L.p, m_tiles, tmem_cols, ablate);
 }
 
 }  // namespace
@@ -298,7 +332,7 @@ void finalize_tc_launch(TcLaunch& L) {
   int total_kb = 0;
   for (int s = 0; s < L.p.nseg; ++s) total_kb += L.p.seg[s].nkb;
   const size_t a_bytes = (size_t)BM_TC * L.BK * 2;
-  const size_t budget = 200 * 1024;
+  const size_t budget = 196 * 1024;
   // conv weights are small: keep the whole [BN x K] operand in shared memory when it leaves room for >= 4 A stages
   L.p.resident = 0;
   if (L.epi_kind == EPI_CONV) {
@@ -317,7 +351,7 @@ void finalize_tc_launch(TcLaunch& L) {
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   L.p.stages = stages;
-  size_t smem = 1024 + bres + (size_t)stages * stage_bytes + 8 * (2 * stages + 6) + 16 + (size_t)L.p.epi.N * 4 + 16;
+  size_t smem = 1024 + bres + (size_t)stages * stage_bytes + 8 * (2 * stages + 6) + 16 + (size_t)L.p.epi.N * 4 + 32 + 8 * 2048;
   // 2*BN TMEM columns per CTA: keep co-resident CTAs within the 512-column budget
   const int cols = 2 * L.p.BN;
   if (cols > 256 && smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM

@@ -37,38 +37,6 @@ __device__ __forceinline__ uint32_t idesc_f16(bool f16, int n) {
   const uint32_t fmt = f16 ? 0u : 1u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// Warp-cooperative store of a [32 rows x NP*8 columns] 16-bit block that the warp holds one row per lane
-// (TMEM layout).  The block is staged through a warp-private 2 KB shared-memory tile (64-byte rows, 16-byte
-// pieces XOR-swizzled by (row >> 1) & 3 so both the row-wise writes and the piece-wise reads are conflict free) and
-// written back with consecutive lanes on consecutive 16-byte pieces: every store instruction covers whole
-// 64-byte (NP = 4) row segments, 8 rows at a time, instead of 32 scattered 16-byte pieces.
-template <int NP>
-__device__ __forceinline__ void staged_store(uint32_t stage, const uint32_t (&pk)[16], int lane, uint32_t ok_mask,
-                                             uint8_t* dst_row0, size_t pitch_bytes) {
-  const uint32_t sw = (uint32_t)((lane >> 1) & 3);
-#pragma unroll
-  for (int pc = 0; pc < NP; ++pc)
-    sts128(stage + (uint32_t)lane * 64u + (((uint32_t)pc ^ sw) << 4), make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]));
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    const int id = j * 32 + lane;
-    const int ri = id / NP, pc = id % NP;
-    const uint4 v = lds128(stage + (uint32_t)ri * 64u + (((uint32_t)pc ^ (uint32_t)((ri >> 1) & 3)) << 4));
-    if ((ok_mask >> ri) & 1u) *reinterpret_cast<uint4*>(dst_row0 + (size_t)ri * pitch_bytes + pc * 16) = v;
-  }
-  __syncwarp();
-}
-
 // ============================================================================================
 // Kernel A
 // ============================================================================================
@@ -80,7 +48,6 @@ constexpr uint32_t A_WB1_BLK = 48 * 64 * 2;            // 6144
 constexpr int A_NKB = 4;
 constexpr uint32_t A_ACC_STRIDE = 256;                 // TMEM columns per accumulator stage (240 used):
                                                        // b1 [0,48) b2 [48,96) b3a [96,128) b4a [128,160) b5a [160,192) stem [192,240)
-constexpr uint32_t EPI_STAGE_BYTES = 32 * 64;          // per epilogue warp
 
 struct ASmem {
   static constexpr uint32_t wp1 = 0;

@@ -105,10 +105,44 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Warp-cooperative store of a [32 rows x NP*8 columns] 16-bit block that the warp holds one row per lane
+// (TMEM layout).  The block is staged through a warp-private 2 KB shared-memory tile (64-byte rows, 16-byte
+// pieces XOR-swizzled by (row >> 1) & 3 so both the row-wise writes and the piece-wise reads are conflict free) and
+// written back with consecutive lanes on consecutive 16-byte pieces: every store instruction covers whole
+// 64-byte (NP = 4) row segments, 8 rows at a time, instead of 32 scattered 16-byte pieces.
+template <int NP>
+__device__ __forceinline__ void staged_store(uint32_t stage, const uint32_t (&pk)[16], int lane, uint32_t ok_mask,
+                                             uint8_t* dst_row0, size_t pitch_bytes) {
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+  for (int pc = 0; pc < NP; ++pc)
+    sts128(stage + (uint32_t)lane * 64u + (((uint32_t)pc ^ sw) << 4), make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const int id = j * 32 + lane;
+    const int ri = id / NP, pc = id % NP;
+    const uint4 v = lds128(stage + (uint32_t)ri * 64u + (((uint32_t)pc ^ (uint32_t)((ri >> 1) & 3)) << 4));
+    if ((ok_mask >> ri) & 1u) *reinterpret_cast<uint4*>(dst_row0 + (size_t)ri * pitch_bytes + pc * 16) = v;
+  }
+  __syncwarp();
+}
+
 // Programmatic dependent launch: let the next kernel of the stream start its prologue while this grid drains,
 // and wait for the previous grid's results before touching them.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+constexpr uint32_t EPI_STAGE_BYTES = 32 * 64;          // staged_store() scratch per epilogue warp
 
 }  // namespace tc
 

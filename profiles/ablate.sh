@@ -1,4 +1,4 @@
-run() { ncu --metrics gpu__time_duration.sum --clock-control none -k regex:incept -s 44 -c 22 --csv python bench.py --steps 1 --warmup 3 --samples-per-step 32768 --max-chunk 32768 --e2e-samples 16384 --no-cpu-baseline 2>/dev/null | grep incept | python -c "
+run() { ncu --metrics gpu__time_duration.sum --clock-control none -k regex:incept -s 44 -c 22 --csv python bench.py --steps 1 --warmup 3 --samples-per-step 32768 --max-chunk 32768 --e2e-samples 16384 --no-cpu-baseline 2>/dev/null | grep '^"[0-9]' | grep incept | python -c "
 import sys,csv
 a=b=0
 for r in csv.reader(sys.stdin):
