@@ -134,3 +134,27 @@ def test_two_rank_sharding_and_host_gather(tmp_path):
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     got = open(os.path.join(str(tmp_path), "merged.txt")).read().splitlines()
     assert got == ["read%d\tline%d" % (r, k) for r in range(11) for k in range(2)]
+
+
+def test_binary_record_layout_matches_reference_struct(tmp_path):
+    """1628-byte record of the reference: struct format '<17B17f17f17H360f1B'
+    (scripts/generate_binary_feature_file.py:52-54)."""
+    import struct
+    from deepsignal_b200 import binary_format as bf
+    from deepsignal_b200.synth import synth_features
+    assert bf.record_dtype().itemsize == 1628 == struct.calcsize("<17B17f17f17H360f1B")
+    f = synth_features(5, seed=3)
+    p = str(tmp_path / "x.bin")
+    bf.write_binary(p, f["kmer"], f["means"], f["stds"], f["lens"], f["signals"], [1, 0, 1, 1, 0])
+    raw = open(p, "rb").read()
+    assert len(raw) == 5 * 1628
+    fmt = "<17B17f17f17H360f1B"
+    for i in range(5):
+        vals = struct.unpack(fmt, raw[i * 1628:(i + 1) * 1628])
+        assert list(vals[:17]) == f["kmer"][i].tolist()
+        assert np.array_equal(np.asarray(vals[17:34], np.float32), f["means"][i])
+        assert list(vals[51:68]) == f["lens"][i].tolist()
+        assert np.array_equal(np.asarray(vals[68:428], np.float32), f["signals"][i])
+    back = bf.read_binary(p)
+    assert np.array_equal(back["kmer"], f["kmer"]) and np.array_equal(back["signals"], f["signals"])
+    assert back["lens"].dtype == np.float32 and back["labels"].tolist() == [1, 0, 1, 1, 0]
