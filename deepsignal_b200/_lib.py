@@ -19,6 +19,7 @@ EXPORTS = [
     "dsb_set_max_chunk", "dsb_workspace_bytes", "dsb_forward_dev", "dsb_forward_host",
     "dsb_set_profiling", "dsb_get_profile", "dsb_launch_count", "dsb_extract_dev",
     "dsb_extract_host", "dsb_extract_max_sites", "dsb_extract_call_dev",
+    "dsb_tsv_parse_features", "dsb_tsv_format_calls",
 ]
 
 
@@ -88,8 +89,12 @@ def load():
     lib.dsb_extract_max_sites.restype = i64
     lib.dsb_extract_call_dev.argtypes = [vp, i32, C.POINTER(Reads), C.POINTER(ExtractParams), C.POINTER(Sites),
                                          C.POINTER(i64), vp, vp, vp]
+    lib.dsb_tsv_parse_features.argtypes = [vp, i64, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), i32]
+    lib.dsb_tsv_parse_features.restype = i64
+    lib.dsb_tsv_format_calls.argtypes = [vp, vp, vp, i32, vp, vp, i64, vp, i64]
+    lib.dsb_tsv_format_calls.restype = i64
     for name in EXPORTS:
-        if name not in ("dsb_last_error", "dsb_workspace_bytes", "dsb_launch_count", "dsb_extract_max_sites",
+        if name not in ("dsb_tsv_parse_features", "dsb_tsv_format_calls", "dsb_last_error", "dsb_workspace_bytes", "dsb_launch_count", "dsb_extract_max_sites",
                         "dsb_abi_version"):
             getattr(lib, name).restype = C.c_int
     _lib = lib

@@ -176,6 +176,28 @@ def call_mods(input_path, model_path, result_file, kmer_len, cent_signals_len,
             pred_str, _, nb = _call_mods(features_batch, engine, model, learning_rate, batch_size)
             pred_str_q.put(pred_str)
             n_batches += nb
+    elif input_path.endswith(".bin"):
+        # the reference's 1628-byte binary sample records (scripts/generate_binary_feature_file.py): no read / position
+        # columns exist in that format, so the six info columns are printed as '.'
+        from .binary_format import read_binary
+        rec = read_binary(input_path, kmer_len, cent_signals_len)
+        step = 1 << 18
+        for lo in range(0, len(rec["labels"]), step):
+            sl = slice(lo, lo + step)
+            n_here = len(rec["labels"][sl])
+            batch = (["\t".join(["."] * 6)] * n_here, rec["kmer"][sl].tolist(), rec["means"][sl], rec["stds"][sl],
+                     rec["lens"][sl], rec["signals"][sl], rec["labels"][sl])
+            pred_str, _, nb = _call_mods(batch, engine, model, learning_rate, batch_size)
+            pred_str_q.put(pred_str)
+            n_batches += nb
+    elif os.environ.get("DSB_PY_TSV", "0") != "1":
+        # fast path: C++ text codec (csrc/tsv.cpp); identical parsing rules and byte-identical result lines
+        from .fast_tsv import iter_feature_blocks, format_calls
+        for block in iter_feature_blocks(input_path, kmer_len, cent_signals_len, nthreads=max(1, nproc)):
+            probs, prediction = engine.forward(block.kmer, block.means, block.stds, block.lens, block.signals,
+                                               precision=model.precision)
+            pred_str_q.put([format_calls(block, probs, prediction).decode().rstrip("\n")])
+            n_batches += -(-block.n // batch_size)
     else:
         features_batch_q = queue.Queue(maxsize=queen_size_border)
         p_rf = threading.Thread(target=_read_features_file, args=(input_path, features_batch_q, f5_batch_num * 64),

@@ -13,6 +13,10 @@ for f in api fold gemm_f32 gemm_tc incept_tc forward extract; do
     pids+=($!)
   fi
 done
+if [ ! -f build/tsv.o ] || [ tsv.cpp -nt build/tsv.o ] || [ ../../include/dsb200.h -nt build/tsv.o ]; then
+  g++ -O3 -std=c++17 -fPIC -fvisibility=hidden -c tsv.cpp -o build/tsv.o &
+  pids+=($!)
+fi
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT build/api.o build/fold.o build/gemm_f32.o build/gemm_tc.o build/incept_tc.o build/forward.o build/extract.o -cudart static
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT build/api.o build/fold.o build/gemm_f32.o build/gemm_tc.o build/incept_tc.o build/forward.o build/extract.o build/tsv.o -cudart static
 echo "built $(realpath $OUT)"

@@ -179,6 +179,21 @@ DSB_API int dsb_extract_call_dev(dsb_ctx* ctx, int32_t precision, const dsb_read
                          const dsb_extract_params* params, const dsb_sites* sites, int64_t* n_sites,
                          float* probs, int32_t* pred, void* cuda_stream);
 
+/* ---- text codec around the path (host only) ---------------------------------------
+ * dsb_tsv_parse_features: parse whole lines of a 12-column feature file (reference
+ * extract_features.py:289-303, reader call_modifications.py:35-91) from buf[0:len) into the model-input
+ * arrays; info_off[i] = byte range of the first six columns of sample i.  Returns the number of samples
+ * (<= max_samples), *consumed = bytes of complete lines eaten; -(1000+i) if line i is malformed.
+ * dsb_tsv_format_calls: render the 10-column call_mods lines (call_modifications.py:183-190) with
+ * numpy-identical float32 text; returns bytes written. */
+DSB_API int64_t dsb_tsv_parse_features(const char* buf, int64_t len, int32_t kmer_len, int32_t signal_len,
+                                       int64_t max_samples, int32_t* kmer, float* means, float* stds, float* lens,
+                                       float* signals, int32_t* labels, int64_t* info_off, int64_t* consumed,
+                                       int32_t nthreads);
+DSB_API int64_t dsb_tsv_format_calls(const char* info_buf, const int64_t* info_off, const int32_t* kmer,
+                                     int32_t kmer_len, const float* probs, const int32_t* pred, int64_t n,
+                                     char* out, int64_t out_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,3 +158,58 @@ def test_binary_record_layout_matches_reference_struct(tmp_path):
     back = bf.read_binary(p)
     assert np.array_equal(back["kmer"], f["kmer"]) and np.array_equal(back["signals"], f["signals"])
     assert back["lens"].dtype == np.float32 and back["labels"].tolist() == [1, 0, 1, 1, 0]
+
+
+def test_fast_tsv_parser_matches_reference_reader(golden):
+    from deepsignal_b200.fast_tsv import iter_feature_blocks
+    a, m = golden
+    p = os.path.join(GOLDEN, "features_small.tsv")
+    blocks = list(iter_feature_blocks(p, max_samples=5, nthreads=2, block_bytes=7000))   # forces carry-over across blocks
+    assert sum(b.n for b in blocks) == 12 and len(blocks) >= 3
+    kmer = np.concatenate([b.kmer for b in blocks])
+    means = np.concatenate([b.means for b in blocks])
+    sig = np.concatenate([b.signals for b in blocks])
+    lens = np.concatenate([b.lens for b in blocks])
+    q = ListQ()
+    cm._read_features_file(p, q, f5_batch_num=10 ** 9)
+    ref = q[0]
+    assert np.array_equal(kmer, np.asarray(ref[1], np.int32))
+    assert np.array_equal(means, np.asarray(ref[2], np.float32))
+    assert np.array_equal(lens, np.asarray(ref[4], np.float32))
+    assert np.array_equal(sig, np.asarray(ref[5], np.float32))
+    infos = []
+    for b in blocks:
+        infos += b.info_strings()
+    assert infos == ref[0]
+    with pytest.raises(ValueError):
+        bad = os.path.join(os.path.dirname(p), "..", "..", "README.md")
+        list(iter_feature_blocks(bad))
+
+
+def test_fast_tsv_formatter_matches_numpy_float32_text(golden):
+    from deepsignal_b200.fast_tsv import iter_feature_blocks, format_calls
+    a, m = golden
+    p = os.path.join(GOLDEN, "features_small.tsv")
+    block = next(iter_feature_blocks(p, max_samples=10 ** 4))
+    fake = a["call_fake_probs"]
+    n0 = len(m["call_pred_str"])
+    got = format_calls(block, np.vstack([fake, fake])[:block.n], np.argmax(np.vstack([fake, fake])[:block.n], axis=1)).decode().splitlines()
+    assert got[:n0] == m["call_pred_str"]                       # byte-identical to the reference's _call_mods output
+    # float32 text == str(np.float32) over many magnitudes
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.random(20000, dtype=np.float32), np.float32(10.0) ** rng.uniform(-12, 0, 20000).astype(np.float32),
+                           np.asarray([0.5, 1.0, 1e-4, 9.9999e-5, 1e-8, 0.99999994, 3.4e-38, 1e-45, 0.0], np.float32)])
+    p1 = vals.astype(np.float32)
+    p0 = (np.float32(1.0) - p1).astype(np.float32)
+    probs = np.stack([p0, p1], axis=1)
+    blk = type(block)()
+    n = len(vals)
+    import ctypes
+    blk.n, blk.kmer, blk.text = n, np.zeros((n, 17), np.int32), b"x"
+    blk.text_ptr = ctypes.cast(ctypes.c_char_p(blk.text), ctypes.c_void_p).value
+    blk.info_off = np.tile(np.asarray([[0, 1]], np.int64), (n, 1))
+    lines = format_calls(blk, probs, np.zeros(n, np.int32)).decode().splitlines()
+    s = p0 + p1
+    for i in range(n):
+        c = lines[i].split("\t")
+        assert c[1] == str(p0[i] / s[i]) and c[2] == str(p1[i] / s[i]), (i, c, str(p0[i] / s[i]), str(p1[i] / s[i]))
