@@ -213,3 +213,27 @@ def test_fast_tsv_formatter_matches_numpy_float32_text(golden):
     for i in range(n):
         c = lines[i].split("\t")
         assert c[1] == str(p0[i] / s[i]) and c[2] == str(p1[i] / s[i]), (i, c, str(p0[i] / s[i]), str(p1[i] / s[i]))
+
+
+def test_tf_bundle_round_trip_and_checkpoint_loader(tmp_path):
+    """SSTable index + data shard written and read back; `load_checkpoint` picks a `.ckpt` prefix up."""
+    from deepsignal_b200 import tf_bundle, weights as W
+    ck = {k: v for k, v in list(W.random_checkpoint(3, "tf_default").items())[:40]}
+    ck["modelglobal_step"] = np.asarray(7, np.int32)            # non-float entries are ignored by the loader
+    prefix = str(tmp_path / "bn_17.sn_360.epoch_9.ckpt")
+    tf_bundle.write_bundle(prefix, ck)
+    idx = tf_bundle.read_index(prefix)
+    assert set(idx) == set(ck)
+    name = "modelsignalmconv_layer1/conv/kernel"
+    assert idx[name]["shape"] == [1, 7, 1, 64] and idx[name]["dtype"] == tf_bundle.DT_FLOAT
+    back = tf_bundle.read_bundle(prefix)
+    for k, v in ck.items():
+        assert back[k].dtype == np.asarray(v).dtype and np.array_equal(back[k], v), k
+    loaded = W.load_checkpoint(prefix)
+    assert "modelglobal_step" not in loaded and np.array_equal(loaded[name], ck[name])
+    assert tf_bundle.crc32c(b"123456789") == 0xE3069283            # CRC-32C check value
+    with open(prefix + ".index", "r+b") as fh:
+        fh.seek(-1, 2)
+        fh.write(b"\x00")
+    with pytest.raises(ValueError):
+        tf_bundle.read_index(prefix)
