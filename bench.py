@@ -308,8 +308,13 @@ def main():
     tc_launches = prof["gemm"]["launches"] + prof["lstm_gemm"]["launches"]
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")      # ncu dram__bytes_{read,write}.sum of the same command, per launch
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            traffic = json.load(fh).get("tensor_core_dram_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gemm_tc_kernel (tcgen05 GEMM + fused conv/LSTM epilogue)",
+                "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu, bytes per tensor-core launch, 32768-sample chunk)", "kernel": "gemm_tc_kernel (tcgen05 GEMM + fused conv/LSTM epilogue)",
                 "launches_profiled": tc_launches, "avg_launch_ms": tc_ms / max(tc_launches, 1),
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                 "breakdown_ms": {k: v["ms"] for k, v in prof.items()},
