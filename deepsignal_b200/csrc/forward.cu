@@ -291,9 +291,9 @@ struct Builder {
               A.p.Lp = Lp; A.p.L = L; A.p.Y = Y; A.p.ldY = YLD; A.p.P3 = TP3; A.p.P4 = TP4; A.p.P5 = TP5; A.p.PS = TPS; A.p.bias = biasA;
               InceptBLaunch& B = sb.ib;
               B.fp16 = f16;
-              encode_map_16(&B.maps.t3, TP3, rows_cap, 32, 32, 128, 32, f16);
-              encode_map_16(&B.maps.t4, TP4, rows_cap, 32, 32, 128, 32, f16);
-              encode_map_16(&B.maps.t5, TP5, rows_cap, 32, 32, 128, 32, f16);
+              encode_map_16(&B.maps.t3, TP3, rows_cap, 32, 32, 136, 32, f16);      // 136-row boxes: taps are row-shifted
+              encode_map_16(&B.maps.t4, TP4, rows_cap, 32, 32, 136, 32, f16);      // descriptors on one staged tile
+              encode_map_16(&B.maps.t5, TP5, rows_cap, 32, 32, 136, 32, f16);
               encode_map_16(&B.maps.w3, Wb3.w, 48, Wb3.Ktot, Wb3.Ktot, 48, 32, f16);
               encode_map_16(&B.maps.w4, Wb4.w, 48, Wb4.Ktot, Wb4.Ktot, 48, 32, f16);
               encode_map_16(&B.maps.w5b, Wb5b.w, 64, Wb5b.Ktot, Wb5b.Ktot, 64, 32, f16);

@@ -285,13 +285,15 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
 // Kernel B
 // ============================================================================================
 constexpr int B_THREADS = 448;       // warp 0 TMA, warp 1 MMA, warps 2-5 branch-5 staging, warps 6-13 epilogue
-constexpr int B_SLOTS = 14;
-constexpr uint32_t B_SLOT_BYTES = 128 * 32 * 2;        // one [128 x 32] SWIZZLE_64B tile
+constexpr int B_SLOTS = 12;                            // ring of plane tiles, 3 per row tile
+constexpr int B_TILE_ROWS = 136;                       // rows r0-2 .. r0+133 of one plane (taps reach r0-2 .. r0+129)
+constexpr uint32_t B_SLOT_BYTES = B_TILE_ROWS * 32 * 2; // one [136 x 32] SWIZZLE_64B tile = 8704 B (17 x 512)
+constexpr uint32_t B_U_BYTES = 128 * 32 * 2;            // one [128 x 32] k-block of the staged relu(b5b) tile
 constexpr uint32_t B_W48_BLK = 48 * 32 * 2;            // 3072
 constexpr uint32_t B_W64_BLK = 64 * 32 * 2;            // 4096
 constexpr uint32_t B_ACC_STRIDE = 160;                 // columns: b3 [0,48) b4 [48,96) b5b [96,160), b5c re-uses [96,144)
 constexpr int B_ACC_STAGES = 3;
-constexpr int B_LOADS = 11;                            // b5b x3, b3 x3, b4 x5
+constexpr int B_LOADS = 3;                             // one tile per plane: P5 (b5b), P3 (b3), P4 (b4)
 
 struct BSmem {
   static constexpr uint32_t w3 = 0;
@@ -299,7 +301,7 @@ struct BSmem {
   static constexpr uint32_t w5b = w4 + 5 * B_W48_BLK;
   static constexpr uint32_t w5c = w5b + 3 * B_W64_BLK;
   static constexpr uint32_t u = w5c + 2 * B_W48_BLK;          // 43008: 3 stages x two [128 x 32] blocks
-  static constexpr uint32_t ring = u + 2 * B_ACC_STAGES * B_SLOT_BYTES;
+  static constexpr uint32_t ring = u + 2 * B_ACC_STAGES * B_U_BYTES;
   static constexpr uint32_t stage = ring + B_SLOTS * B_SLOT_BYTES;          // 8 epilogue warps x 2 KB
   static constexpr uint32_t bars = stage + 8 * EPI_STAGE_BYTES;
   // barriers: full[S] empty[S] wbar b5b_full[3] u_full[3] tfull[3] tempty[3]
@@ -356,16 +358,14 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * 128;
-        // order of consumption: b5b taps (plane P5), b3 taps (P3), b4 taps (P4)
+        // one [136 x 32] tile per plane (rows r0-2 ...), in the order of consumption P5, P3, P4.  The taps of the
+        // 1x3 / 1x5 convs are realised by the MMA issuer with row-shifted operand descriptors on this single tile
+        // (the UMMA swizzle is a function of the absolute shared-memory address: profiles/experiments/umma_shift.cu).
         for (int l = 0; l < B_LOADS; ++l) {
-          const CUtensorMap* mp;
-          int drow;
-          if (l < 3) { mp = &maps.t5; drow = l - 1; }
-          else if (l < 6) { mp = &maps.t3; drow = l - 4; }
-          else { mp = &maps.t4; drow = l - 8; }
+          const CUtensorMap* mp = l == 0 ? &maps.t5 : l == 1 ? &maps.t3 : &maps.t4;
           mbar_wait(empty(slot), phase ^ 1u);
           mbar_expect_tx(full(slot), B_SLOT_BYTES);
-          tma_load_2d(base + BSmem::ring + slot * B_SLOT_BYTES, mp, full(slot), 0, row0 + drow);
+          tma_load_2d(base + BSmem::ring + slot * B_SLOT_BYTES, mp, full(slot), 0, row0 - 2);
           if (++slot == B_SLOTS) { slot = 0; phase ^= 1u; }
         }
       }
@@ -377,27 +377,29 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
       mbar_wait(wbar, 0);
       int slot = 0;
       uint32_t phase = 0;
-      auto run = [&](int ntaps, uint32_t w_off, uint32_t w_blk, uint32_t d, uint32_t idesc) {
+      // all taps of one branch read the same plane tile at row offsets first_row .. first_row + ntaps - 1
+      auto run = [&](int ntaps, int first_row, uint32_t w_off, uint32_t w_blk, uint32_t d, uint32_t idesc) {
+        mbar_wait(full(slot), phase);
+        tc_fence_after();
+        const uint32_t tile = base + BSmem::ring + slot * B_SLOT_BYTES;
         for (int t = 0; t < ntaps; ++t) {
-          mbar_wait(full(slot), phase);
-          tc_fence_after();
-          const uint64_t ad = make_kmajor_desc<32>(base + BSmem::ring + slot * B_SLOT_BYTES);
+          const uint64_t ad = make_kmajor_desc<32>(tile + (uint32_t)(first_row + t) * 64u);
           const uint64_t bd = make_kmajor_desc<32>(base + w_off + t * w_blk);
 #pragma unroll
           for (int k = 0; k < 2; ++k) tc_mma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (t | k) != 0 ? 1u : 0u);
-          tc_commit(empty(slot));
-          if (++slot == B_SLOTS) { slot = 0; phase ^= 1u; }
         }
+        tc_commit(empty(slot));
+        if (++slot == B_SLOTS) { slot = 0; phase ^= 1u; }
       };
       // tap GEMMs of one tile into accumulator stage `a`: branch 5 first so its staging starts early
       auto front = [&](int a, uint32_t a_phase) {
         mbar_wait(tempty(a), a_phase ^ 1u);
         tc_fence_after();
         const uint32_t d0 = tmem_base + a * B_ACC_STRIDE;
-        run(3, BSmem::w5b, B_W64_BLK, d0 + 96, id64);
+        run(3, 1, BSmem::w5b, B_W64_BLK, d0 + 96, id64);     // 1x3: rows r0-1 .. r0+1  (tile row 0 = r0-2)
         tc_commit(b5b_full(a));
-        run(3, BSmem::w3, B_W48_BLK, d0, id48);
-        run(5, BSmem::w4, B_W48_BLK, d0 + 48, id48);
+        run(3, 1, BSmem::w3, B_W48_BLK, d0, id48);
+        run(5, 0, BSmem::w4, B_W48_BLK, d0 + 48, id48);        // 1x5: rows r0-2 .. r0+2
       };
       // software pipeline across tiles: the tap GEMMs of tile i+1 are issued before waiting for the staged
       // relu(b5b) tile of tile i, so the TMEM -> smem round trip of branch 5 is off the critical path.
@@ -412,7 +414,7 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
         mbar_wait(u_full(acc), acc_phase);                // relu(b5b) tile of this stage is in shared memory
         tc_fence_after();
         for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t ad = make_kmajor_desc<32>(base + BSmem::u + (2 * acc + kb) * B_SLOT_BYTES);
+          const uint64_t ad = make_kmajor_desc<32>(base + BSmem::u + (2 * acc + kb) * B_U_BYTES);
           const uint64_t bd = make_kmajor_desc<32>(base + BSmem::w5c + kb * B_W48_BLK);
 #pragma unroll
           for (int k = 0; k < 2; ++k) tc_mma_bf16(d0 + 96, ad + 2 * k, bd + 2 * k, id48, (kb | k) != 0 ? 1u : 0u);
@@ -442,7 +444,7 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
         // k-block kb of U: row i is 64 bytes; logical 16-byte chunk c sits at c ^ ((i >> 1) & 3)  (SWIZZLE_64B)
-        const uint32_t ub = base + BSmem::u + (2 * acc + kb) * B_SLOT_BYTES + (uint32_t)i * 64u;
+        const uint32_t ub = base + BSmem::u + (2 * acc + kb) * B_U_BYTES + (uint32_t)i * 64u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[4];
