@@ -28,6 +28,8 @@ struct Step {
   // GEMM
   GemmF32Params f32;
   TcLaunch tc;
+  CUtensorMap b_half;         // LSTM weights with a 128-row box (CTA-pair kernel)
+  bool pair = false;
   InceptALaunch ia;
   InceptBLaunch ib;
   int epi_kind = EPI_CONV;
@@ -175,6 +177,11 @@ struct Builder {
       L.flops_per_row = st.flops_per_row;
       finalize_tc_launch(L);      // may shrink BN so that the weights stay resident in shared memory
       encode_map_16(&L.maps.b, W.w, W.N, W.Ktot, W.Ktot, L.p.BN, BK, std::is_same<T, __half>::value);
+      if (epi_kind == EPI_LSTM) {
+        const char* ev = getenv("DSB_LSTM_2CTA");      // opt-in while the CTA-pair kernel is being validated
+        st.pair = ev && ev[0] == '1';
+        encode_map_16(&st.b_half, W.w, W.N, W.Ktot, W.Ktot, 128, BK, std::is_same<T, __half>::value);
+      }
     }
     plan.steps.push_back(st);
   }
@@ -508,7 +515,8 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
           g.rows_valid = (int)M;
           launch_gemm_f32(g, st.epi_kind, s);
         } else {
-          launch_gemm_tc(st.tc, (int)M, sms[st.stream], s);
+          if (st.pair) launch_gemm_tc2_lstm(st.tc, st.b_half, (int)M, sms[st.stream], s);
+          else launch_gemm_tc(st.tc, (int)M, sms[st.stream], s);
         }
         ctx->launches++;
         break;

@@ -41,5 +41,7 @@ void encode_map_16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
                    int box_rows, int box_cols, bool fp16);
 void finalize_tc_launch(TcLaunch& L);                       // picks stages / smem
 void launch_gemm_tc(const TcLaunch& L, int M, int sm_count, cudaStream_t s);
+// CTA-pair (tcgen05 cta_group::2) variant of the LSTM step GEMM; b_half = weights map with a 128-row box.
+void launch_gemm_tc2_lstm(const TcLaunch& L, const CUtensorMap& b_half, int M, int sm_count, cudaStream_t s);
 
 }  // namespace dsb
