@@ -200,11 +200,14 @@ gemm_tc2_lstm_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, 
             const float cpv[4] = {cprev[i].x, cprev[i].y, cprev[i].z, cprev[i].w};
             float cn[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b = *reinterpret_cast<const float4*>(sbias + col + 16 * i + 4 * j);
-              lstm_unit<true>(__uint_as_float(r[i][4 * j + 0]) + b.x, __uint_as_float(r[i][4 * j + 1]) + b.y,
-                              __uint_as_float(r[i][4 * j + 2]) + b.z, __uint_as_float(r[i][4 * j + 3]) + b.w,
-                              cpv[j], cn[j], hn[4 * i + j]);
+            for (int j = 0; j < 4; j += 2) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sbias + col + 16 * i + 4 * j);
+              const float4 b1 = *reinterpret_cast<const float4*>(sbias + col + 16 * i + 4 * j + 4);
+              const float za[4] = {__uint_as_float(r[i][4 * j + 0]) + b0.x, __uint_as_float(r[i][4 * j + 1]) + b0.y,
+                                   __uint_as_float(r[i][4 * j + 2]) + b0.z, __uint_as_float(r[i][4 * j + 3]) + b0.w};
+              const float zb[4] = {__uint_as_float(r[i][4 * j + 4]) + b1.x, __uint_as_float(r[i][4 * j + 5]) + b1.y,
+                                   __uint_as_float(r[i][4 * j + 6]) + b1.z, __uint_as_float(r[i][4 * j + 7]) + b1.w};
+              lstm_unit_pair_fast(za, zb, cpv[j], cpv[j + 1], cn[j], cn[j + 1], hn[4 * i + j], hn[4 * i + j + 1]);
             }
             cblk[i * 32] = make_float4(cn[0], cn[1], cn[2], cn[3]);
           }
