@@ -179,6 +179,30 @@ def main():
     meta["call_pred_str"] = pred_str
     out["call_fake_probs"] = fake_probs
 
+    # ---- post-processing: the reference's own frequency script on a synthetic call_mods file ----
+    import subprocess
+    rng2 = np.random.default_rng(4)
+    lines = []
+    for i in range(400):
+        chrom_i = ["chrA", "chrB", "chr10", "chr2"][rng2.integers(0, 4)]
+        pos_i = int(rng2.integers(100, 140))
+        p1 = float(np.float32(rng2.random()))
+        p0 = float(np.float32(1 - p1))
+        lines.append("\t".join([chrom_i, str(pos_i), "+-"[pos_i % 2], str(pos_i + 7), "read%d" % i, "t", str(np.float32(p0)),
+                                 str(np.float32(p1)), str(int(p1 > p0)), "ACGTACGTCGACGTACG"]))
+    calls = os.path.join(HERE, "calls_small.tsv")
+    with open(calls, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    freq = {}
+    for tag, extra in (("plain", []), ("sort", ["--sort"]), ("bed", ["--sort", "--bed"]), ("cf", ["--prob_cf", "0.3"])):
+        tmp_out = os.path.join(HERE, "_freq_tmp.txt")
+        subprocess.check_call([sys.executable, os.path.join(REF, "scripts", "call_modification_frequency.py"), "-i", calls,
+                               "-o", tmp_out] + extra, cwd=os.path.join(REF, "scripts"), stdout=subprocess.DEVNULL)
+        freq[tag] = open(tmp_out).read()
+        os.remove(tmp_out)
+    with open(os.path.join(HERE, "freq_ref.json"), "w") as fh:
+        json.dump(freq, fh)
+
     np.savez_compressed(os.path.join(HERE, "features_ref.npz"), **out)
     with open(os.path.join(HERE, "features_ref.json"), "w") as fh:
         json.dump(meta, fh, indent=0)

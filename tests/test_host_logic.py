@@ -237,3 +237,16 @@ def test_tf_bundle_round_trip_and_checkpoint_loader(tmp_path):
         fh.write(b"\x00")
     with pytest.raises(ValueError):
         tf_bundle.read_index(prefix)
+
+
+def test_site_frequency_matches_reference_script(tmp_path):
+    """call_modification_frequency: byte-identical to the reference script's output (golden from make_golden.py)."""
+    import json
+    from deepsignal_b200 import call_modification_frequency as cmf
+    ref = json.load(open(os.path.join(GOLDEN, "freq_ref.json")))
+    src = os.path.join(GOLDEN, "calls_small.tsv")
+    for tag, (cf, srt, bed) in dict(plain=(0.0, False, False), sort=(0.0, True, False), bed=(0.0, True, True), cf=(0.3, False, False)).items():
+        _, stats = cmf.calculate_mods_frequency([src], cf)
+        out = str(tmp_path / (tag + ".txt"))
+        cmf.write_sitekey2stats(stats, out, srt, bed)
+        assert open(out).read() == ref[tag], tag
