@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--samples-per-step", type=int, default=1 << 20)
     ap.add_argument("--e2e-samples", type=int, default=1 << 19)
     ap.add_argument("--max-chunk", type=int, default=32768)
-    ap.add_argument("--cpu-samples", type=int, default=2048)
+    ap.add_argument("--cpu-samples", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="forward", choices=["forward", "extract", "e2e"],
                     help="forward = BASELINE configs[2] (default, the metric's workload); extract = configs[1] "
@@ -218,7 +218,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        per_step = max(512, a.cpu_samples // 2)
+        per_step = max(512, a.cpu_samples // 4)
         for _ in range(max(1, min(a.warmup, 1))):
             cpu_baseline(512, ckpt)
         t_tot, n_tot = 0.0, 0
