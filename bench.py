@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--samples-per-step", type=int, default=1 << 20)
     ap.add_argument("--e2e-samples", type=int, default=1 << 19)
-    ap.add_argument("--max-chunk", type=int, default=32768)
+    ap.add_argument("--max-chunk", type=int, default=37888)
     ap.add_argument("--cpu-samples", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="forward", choices=["forward", "extract", "e2e"],

@@ -170,7 +170,7 @@ struct dsb_ctx {
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   std::string err;
-  int64_t max_chunk = 32768;
+  int64_t max_chunk = 37888;   // 148 SMs x 256 samples: the persistent LSTM kernel gives every SM exactly two item pairs
   int64_t launches = 0;
   bool have_model = false;
   dsb::FoldedModel model;

@@ -14,10 +14,11 @@
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
 #include "incept_tc.cuh"
+#include "lstm_seq.cuh"
 
 namespace dsb {
 
-enum StepKind { ST_GEMM, ST_STEM, ST_POOL1, ST_POOL2, ST_FEAT, ST_HEAD, ST_ZERO, ST_INCEPT_A, ST_INCEPT_B };
+enum StepKind { ST_GEMM, ST_STEM, ST_POOL1, ST_POOL2, ST_FEAT, ST_HEAD, ST_ZERO, ST_INCEPT_A, ST_INCEPT_B, ST_LSTM_SEQ };
 
 struct SegHost { const void* a; int ld; int cols; int col0; int drow; int K; int map_rows_per_sample; };
 
@@ -32,6 +33,7 @@ struct Step {
   bool pair = false;
   InceptALaunch ia;
   InceptBLaunch ib;
+  LstmSeqLaunch seq;
   int epi_kind = EPI_CONV;
   int kclass = KC_GEMM;
   double flops_per_row = 0;
@@ -373,45 +375,85 @@ struct Builder {
         st.stream = 0;    // runs before the fork
         plan.steps.insert(plan.steps.begin(), st);
       }
-      for (int d = 0; d < 2; ++d) {
-        T* H[NLAYER];
-        float* Cst[NLAYER];
+      T* H[2][NLAYER];
+      float* Cst[2][NLAYER];
+      DevGemm<T> Wl[2][NLAYER];
+      for (int d = 0; d < 2; ++d)
         for (int l = 0; l < NLAYER; ++l) {
-          H[l] = buf((size_t)(KL + 1) * cap * HID);
-          Cst[l] = reinterpret_cast<float*>(ba.take((size_t)cap * HID * sizeof(float)));
-          Step z;
-          z.kind = ST_ZERO;
-          z.stream = 1 + d;
-          z.dst = H[l]; z.zero_bytes_per_sample = HID * sizeof(T);      // slot 0 = h_init
-          plan.steps.push_back(z);
-          Step zc = z;
-          zc.dst = Cst[l]; zc.zero_bytes_per_sample = HID * sizeof(float);
-          plan.steps.push_back(zc);
-        }
-        for (int l = 0; l < NLAYER; ++l) {
-          DevGemm<T> Wl = (l == 0)
+          H[d][l] = buf((size_t)(KL + 1) * cap * HID);
+          Cst[d][l] = reinterpret_cast<float*>(ba.take((size_t)cap * HID * sizeof(float)));
+          Wl[d][l] = (l == 0)
               ? upload_gemm<T>(wa, fm.lstm[d][l].g, std::vector<std::array<int, 3>>{{0, HID, HID}, {HID, 8, FW}}, up_stream)
               : upload_gemm<T>(wa, fm.lstm[d][l].g, std::vector<std::array<int, 3>>{{0, HID, HID}, {HID, HID, HID}}, up_stream);
-          for (int t = 0; t < KL; ++t) {
-            const int pos = (d == 0) ? t : KL - 1 - t;          // bw consumes the k-mer reversed
-            T* hprev = H[l] + (size_t)t * cap * HID;
-            T* hnext = H[l] + (size_t)(t + 1) * cap * HID;
-            EpiParams e;
-            e.c = Cst[l];
-            e.h_out = hnext;
-            std::vector<SegHost> segs;
-            if (l == 0) {
-              segs.push_back(SegHost{hprev, HID, HID, 0, 0, HID, 1});
-              segs.push_back(SegHost{F + (size_t)pos * cap * FW, FW, FW, 0, 0, FW, 1});
-            } else {
-              segs.push_back(SegHost{H[l - 1] + (size_t)(t + 1) * cap * HID, HID, HID, 0, 0, HID, 1});
-              segs.push_back(SegHost{hprev, HID, HID, 0, 0, HID, 1});
+        }
+      bool seq = false;
+      if constexpr (TC) {
+        const char* ev = getenv("DSB_LSTM_SEQ");      // DSB_LSTM_SEQ=0 keeps one launch per (direction, layer, step) (A/B tests)
+        seq = !(ev && ev[0] == '0') && NLAYER == LSTM_SEQ_LAYERS;
+      }
+      if (seq) {
+        if constexpr (TC) {
+          // one persistent kernel for all directions, layers and time steps of the chunk (lstm_seq.cu)
+          Step st;
+          st.kind = ST_LSTM_SEQ;
+          st.stream = 1;
+          st.rows_per_sample = 1;
+          st.kclass = KC_LSTM;
+          st.flops_per_row = 2.0 * 2.0 * (double)KL * (double)GATES * ((double)HID + 2.0 * (2.0 * HID));
+          if (place) {
+            const bool f16 = std::is_same<T, __half>::value;
+            LstmSeqLaunch& Q = st.seq;
+            Q.fp16 = f16;
+            encode_map_16(&Q.maps.f, F, (int64_t)KL * cap, FW, FW, 128, 64, f16);
+            for (int d = 0; d < 2; ++d) {
+              Q.p.c[d] = Cst[d][0];
+              for (int l = 0; l < NLAYER; ++l) {
+                encode_map_16(&Q.maps.h[d][l], H[d][l], (int64_t)(KL + 1) * cap, HID, HID, 128, 64, f16);
+                encode_map_16(&Q.maps.w[d][l], Wl[d][l].w, GATES, Wl[d][l].Ktot, Wl[d][l].Ktot, 256, 64, f16);
+                Q.p.bias[d][l] = Wl[d][l].bias;
+                Q.p.H[d][l] = H[d][l];
+              }
             }
-            gemm(1 + d, 1, cap, segs, Wl, 64, e, EPI_LSTM, KC_LSTM, 1, l == 0 ? HID : 2 * HID);
+            Q.p.cap = cap;
+            Q.p.KL = KL;
+          }
+          plan.steps.push_back(st);
+        }
+      } else {
+        for (int d = 0; d < 2; ++d) {
+          for (int l = 0; l < NLAYER; ++l) {
+            Step z;
+            z.kind = ST_ZERO;
+            z.stream = 1 + d;
+            z.dst = H[d][l]; z.zero_bytes_per_sample = HID * sizeof(T);      // slot 0 = h_init
+            plan.steps.push_back(z);
+            Step zc = z;
+            zc.dst = Cst[d][l]; zc.zero_bytes_per_sample = HID * sizeof(float);
+            plan.steps.push_back(zc);
+          }
+          for (int l = 0; l < NLAYER; ++l) {
+            for (int t = 0; t < KL; ++t) {
+              const int pos = (d == 0) ? t : KL - 1 - t;          // bw consumes the k-mer reversed
+              T* hprev = H[d][l] + (size_t)t * cap * HID;
+              T* hnext = H[d][l] + (size_t)(t + 1) * cap * HID;
+              EpiParams e;
+              e.c = Cst[d][l];
+              e.h_out = hnext;
+              std::vector<SegHost> segs;
+              if (l == 0) {
+                segs.push_back(SegHost{hprev, HID, HID, 0, 0, HID, 1});
+                segs.push_back(SegHost{F + (size_t)pos * cap * FW, FW, FW, 0, 0, FW, 1});
+              } else {
+                segs.push_back(SegHost{H[d][l - 1] + (size_t)(t + 1) * cap * HID, HID, HID, 0, 0, HID, 1});
+                segs.push_back(SegHost{hprev, HID, HID, 0, 0, HID, 1});
+              }
+              gemm(1 + d, 1, cap, segs, Wl[d][l], 64, e, EPI_LSTM, KC_LSTM, 1, l == 0 ? HID : 2 * HID);
+            }
           }
         }
-        (d == 0 ? hfw : hbw) = H[NLAYER - 1] + (size_t)KL * cap * HID;
       }
+      hfw = H[0][NLAYER - 1] + (size_t)KL * cap * HID;
+      hbw = H[1][NLAYER - 1] + (size_t)KL * cap * HID;
     }
 
     // head
@@ -533,6 +575,14 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
         if constexpr (!std::is_same<T, float>::value) {
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
           launch_incept_b(st.ib, (int)M, sms[st.stream], s);
+          ctx->launches++;
+        }
+        break;
+      }
+      case ST_LSTM_SEQ: {
+        if constexpr (!std::is_same<T, float>::value) {
+          Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
+          launch_lstm_seq(st.seq, (int)n, sms[st.stream], s);
           ctx->launches++;
         }
         break;

@@ -202,3 +202,21 @@ def test_fused_inception_kernels_match_unfused_launches(engine, ckpt, precision,
     d = np.abs(a - b).max()
     print("\n[fused vs unfused, {}] max|dp|={:.3e} identical={}".format(precision, d, np.array_equal(a, b)))
     assert d <= 1e-3
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("n", [110, 700])
+def test_persistent_lstm_kernel_matches_per_step_launches(engine, ckpt, precision, n, monkeypatch):
+    """lstm_seq.cu (one launch for all directions / layers / steps) against the 102 per-step GEMM launches:
+    same K layout and segment order, so the probabilities must be bit-identical."""
+    x = _inputs(4321, n)
+    monkeypatch.setenv("DSB_LSTM_SEQ", "0")
+    engine.load_weights(ckpt)
+    a, pa = engine.forward(*x, precision=precision)
+    monkeypatch.setenv("DSB_LSTM_SEQ", "1")
+    engine.load_weights(ckpt)
+    b, pb = engine.forward(*x, precision=precision)
+    d = np.abs(a - b).max()
+    print("\n[lstm seq vs per-step, {}, n={}] max|dp|={:.3e} identical={}".format(precision, n, d, np.array_equal(a, b)))
+    assert np.array_equal(a, b)
+    assert np.array_equal(pa, pb)
