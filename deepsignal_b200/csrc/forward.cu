@@ -8,6 +8,7 @@
 // conv is a sum of row-shifted GEMMs and a sample never sees its neighbour.
 #include <algorithm>
 #include <array>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -15,10 +16,11 @@
 #include "gemm_tc.cuh"
 #include "incept_tc.cuh"
 #include "lstm_seq.cuh"
+#include "front_tc.cuh"
 
 namespace dsb {
 
-enum StepKind { ST_GEMM, ST_STEM, ST_POOL1, ST_POOL2, ST_FEAT, ST_HEAD, ST_ZERO, ST_INCEPT_A, ST_INCEPT_B, ST_LSTM_SEQ };
+enum StepKind { ST_GEMM, ST_STEM, ST_POOL1, ST_POOL2, ST_FEAT, ST_HEAD, ST_ZERO, ST_INCEPT_A, ST_INCEPT_B, ST_LSTM_SEQ, ST_FRONT, ST_DEBUG_CMP };
 
 struct SegHost { const void* a; int ld; int cols; int col0; int drow; int K; int map_rows_per_sample; };
 
@@ -34,6 +36,7 @@ struct Step {
   InceptALaunch ia;
   InceptBLaunch ib;
   LstmSeqLaunch seq;
+  FrontLaunch front;
   int epi_kind = EPI_CONV;
   int kclass = KC_GEMM;
   double flops_per_row = 0;
@@ -55,6 +58,7 @@ struct ForwardPlan {
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   bool multi_stream = true;
   size_t work_bytes = 0;
+  std::vector<std::pair<const char*, std::pair<const void*, size_t>>> dbg;   // DSB_DEBUG_SUM: named buffers to checksum after each step
   ~ForwardPlan() {
     for (auto s : side) if (s) cudaStreamDestroy(s);
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -65,6 +69,25 @@ struct ForwardPlan {
 void destroy_plan(ForwardPlan* p) { delete p; }
 
 namespace {
+
+// debug aid (DSB_FRONT_CHECK=1): compare two 16-bit [rows][ld] buffers on cols [0, C), report mismatches
+__global__ void debug_compare_kernel(const uint16_t* a, const uint16_t* b, long long rows, int C, int ld, int Lp, int* count) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * C) return;
+  const long long r = idx / C;
+  const int c = (int)(idx % C);
+  const uint16_t x = a[r * ld + c], y = b[r * ld + c];
+  if (x != y) {
+    const int k = atomicAdd(count, 1);
+    if (k < 24) printf("front mismatch row %lld (sample %lld pos %lld) col %d: fused %04x separate %04x\n", r, r / Lp, r % Lp, c, x, y);
+  }
+}
+
+__global__ void debug_sum_kernel(const uint16_t* a, long long n, unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += a[i] * (unsigned long long)(1 + (i & 1023));
+  atomicAdd(out, acc);
+}
 
 struct Arena {          // bump allocator over one DevBuf (two passes: size, then place)
   uint8_t* base = nullptr;
@@ -223,6 +246,7 @@ struct Builder {
       T* P1 = buf((size_t)R2 * 64);
       T* C2 = buf((size_t)R2 * 128);
       T* X0 = buf((size_t)R2 * 256);
+      T* X0_main = X0;
       T* XP = buf((size_t)R2 * 256);
       constexpr int YLD = 256;            // 240 channels padded to a 512-byte row pitch: every TMA row chunk is one aligned 128-byte line
       T* YA = buf((size_t)R2 * YLD);
@@ -234,24 +258,69 @@ struct Builder {
       T* Tb = buf((size_t)R2 * 144);
       T* Ub = buf((size_t)R2 * 64);
 
-      // stem
-      {
-        Step st;
-        st.kind = ST_STEM;
-        st.stream = 0;
-        const int conv_total = std::max((fm.L1 - 1) * 2 + 7 - S, 0);
-        const int pool_total = std::max((L2 - 1) * 2 + 3 - fm.L1, 0);
-        st.stem = StemParams{nullptr, S, w1, b1, fm.L1, L2, Lp2, conv_total / 2, pool_total / 2, P1, 0};
-        plan.steps.push_back(st);
+      if (place) {
+        plan.dbg = {{"P1", {P1, (size_t)R2 * 64}}, {"C2", {C2, (size_t)R2 * 128}}, {"X0", {X0, (size_t)R2 * 256}}, {"YA", {YA, (size_t)R2 * YLD}}, {"YB", {YB, (size_t)R2 * YLD}},
+                    {"TP3", {TP3, (size_t)R2 * 32}}, {"TP4", {TP4, (size_t)R2 * 32}}, {"TP5", {TP5, (size_t)R2 * 32}}, {"TPS", {TPS, (size_t)R2 * 48}}};
       }
       auto conv_epi = [&](void* d0, int ld0, int c0, uint32_t relu, int Lp, int L) {
         EpiParams e;
         e.d0 = d0; e.ld0 = ld0; e.c0 = c0; e.split = 1 << 30; e.relu_mask = relu; e.Lp = Lp; e.L = L;
         return e;
       };
-      gemm(0, Lp2, R2, {SegHost{P1, 64, 64, 0, 0, 64, Lp2}}, Wc2, 64, conv_epi(C2, 128, 0, 0xffffffffu, Lp2, L2), EPI_CONV, KC_GEMM, L2, 64);
-      gemm(0, Lp2, R2, {SegHost{C2, 128, 128, 0, -1, 128, Lp2}, SegHost{C2, 128, 128, 0, 0, 128, Lp2}, SegHost{C2, 128, 128, 0, 1, 128, Lp2}},
-           Wc3, 64, conv_epi(X0, 256, 0, 0xffffffffu, Lp2, L2), EPI_CONV, KC_GEMM, L2, 384);
+      const int conv_total = std::max((fm.L1 - 1) * 2 + 7 - S, 0);
+      const int pool_total = std::max((L2 - 1) * 2 + 3 - fm.L1, 0);
+      bool front = false;
+      if constexpr (TC) {
+        const char* ev = getenv("DSB_FRONT");        // DSB_FRONT=0 keeps stem_kernel + two GEMM launches (A/B tests)
+        front = !(ev && ev[0] == '0');
+      }
+      if (front) {
+        if constexpr (TC) {
+          // conv1 + pool + conv2 + conv3 in one kernel (front_tc.cu): P1 and C2 stay in shared memory
+          Step st;
+          st.kind = ST_FRONT;
+          st.stream = 0;
+          st.rows_per_sample = Lp2;
+          st.kclass = KC_GEMM;
+          st.flops_per_row = 2.0 * (64.0 * 128.0 + 384.0 * 256.0) * (double)L2 / (double)Lp2;
+          if (place) {
+            const bool f16 = std::is_same<T, __half>::value;
+            FrontLaunch& Q = st.front;
+            Q.fp16 = f16;
+            encode_map_16(&Q.maps.w2, Wc2.w, 128, Wc2.Ktot, Wc2.Ktot, 128, 64, f16);
+            if (Wc3.N != 256 || Wc2.N != 128) fail(DSB_ERR_STATE, "internal: front kernel expects conv2 N=128, conv3 N=256");
+            encode_map_16(&Q.maps.w3, Wc3.w, 256, Wc3.Ktot, Wc3.Ktot, 128, 32, f16);
+            Q.p.S = S; Q.p.w1 = w1; Q.p.b1 = b1; Q.p.b2 = Wc2.bias; Q.p.b3 = Wc3.bias;
+            Q.p.L1 = fm.L1; Q.p.L = L2; Q.p.Lp = Lp2; Q.p.conv_pl = conv_total / 2; Q.p.pool_pl = pool_total / 2;
+            Q.p.X0 = X0; Q.p.ldX = 256;
+          }
+          plan.steps.push_back(st);
+        }
+      }
+      const bool front_check = getenv("DSB_FRONT_CHECK") != nullptr;
+      T* X0ref = front_check ? buf((size_t)R2 * 256) : nullptr;
+      if (place && front_check) plan.dbg.push_back({"X0ref", {X0ref, (size_t)R2 * 256}});
+      if (!front || front_check) {
+        T* X0 = front_check ? X0ref : X0_main;
+        {
+          Step st;
+          st.kind = ST_STEM;
+          st.stream = 0;
+          st.stem = StemParams{nullptr, S, w1, b1, fm.L1, L2, Lp2, conv_total / 2, pool_total / 2, P1, 0};
+          plan.steps.push_back(st);
+        }
+        gemm(0, Lp2, R2, {SegHost{P1, 64, 64, 0, 0, 64, Lp2}}, Wc2, 64, conv_epi(C2, 128, 0, 0xffffffffu, Lp2, L2), EPI_CONV, KC_GEMM, L2, 64);
+        gemm(0, Lp2, R2, {SegHost{C2, 128, 128, 0, -1, 128, Lp2}, SegHost{C2, 128, 128, 0, 0, 128, Lp2}, SegHost{C2, 128, 128, 0, 1, 128, Lp2}},
+             Wc3, 64, conv_epi(X0, 256, 0, 0xffffffffu, Lp2, L2), EPI_CONV, KC_GEMM, L2, 384);
+        if (front_check) {
+          Step st;
+          st.kind = ST_DEBUG_CMP;
+          st.stream = 0;
+          st.rows_per_sample = Lp2;
+          st.src = X0_main; st.dst = X0ref; st.C = 192; st.ld = 256; st.Lpin = Lp2;
+          plan.steps.push_back(st);
+        }
+      }
 
       const T* X = X0;
       int xld = 256;
@@ -410,6 +479,7 @@ struct Builder {
               for (int l = 0; l < NLAYER; ++l) {
                 encode_map_16(&Q.maps.h[d][l], H[d][l], (int64_t)(KL + 1) * cap, HID, HID, 128, 64, f16);
                 encode_map_16(&Q.maps.w[d][l], Wl[d][l].w, GATES, Wl[d][l].Ktot, Wl[d][l].Ktot, 256, 64, f16);
+                encode_map_16(&Q.maps.w2[d][l], Wl[d][l].w, GATES, Wl[d][l].Ktot, Wl[d][l].Ktot, 128, 64, f16);
                 Q.p.bias[d][l] = Wl[d][l].bias;
                 Q.p.H[d][l] = H[d][l];
               }
@@ -538,6 +608,20 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
     if (debug_sync && step_idx > 0) {
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) fail(DSB_ERR_CUDA, "step %d (kind %d) failed: %s", step_idx - 1, plan.steps[step_idx - 1].kind, cudaGetErrorString(e));
+      if (getenv("DSB_DEBUG_SUM")) {
+        unsigned long long* d = nullptr;
+        cudaMalloc(&d, 8);
+        fprintf(stderr, "[sum] after step %d kind %d:", step_idx - 1, plan.steps[step_idx - 1].kind);
+        for (auto& b : plan.dbg) {
+          cudaMemset(d, 0, 8);
+          debug_sum_kernel<<<256, 256>>>(reinterpret_cast<const uint16_t*>(b.second.first), (long long)b.second.second, d);
+          unsigned long long h = 0;
+          cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+          fprintf(stderr, " %s=%llx", b.first, h);
+        }
+        fprintf(stderr, "\n");
+        cudaFree(d);
+      }
     }
     cudaStream_t s = streams[st.stream];
     if (multi && !forked && st.kind != ST_FEAT) {
@@ -582,9 +666,34 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_LSTM_SEQ: {
         if constexpr (!std::is_same<T, float>::value) {
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
-          launch_lstm_seq(st.seq, (int)n, sms[st.stream], s);
+          static const bool lstm_pair = getenv("DSB_LSTM_PAIR") && getenv("DSB_LSTM_PAIR")[0] == '1';
+          if (lstm_pair) launch_lstm_seq2(st.seq, (int)n, sms[st.stream], s);
+          else launch_lstm_seq(st.seq, (int)n, sms[st.stream], s);
           ctx->launches++;
         }
+        break;
+      }
+      case ST_FRONT: {
+        if constexpr (!std::is_same<T, float>::value) {
+          Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
+          launch_front(st.front, signals, (int)n, sms[st.stream], s);
+          ctx->launches++;
+        }
+        break;
+      }
+      case ST_DEBUG_CMP: {
+        int* cnt = nullptr;
+        DSB_CUDA(cudaMalloc(&cnt, sizeof(int)));
+        DSB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), s));
+        const long long rows_all = plan.cap * st.rows_per_sample;
+        const long long total = rows_all * 256;
+        debug_compare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint16_t*>(st.src), reinterpret_cast<const uint16_t*>(st.dst),
+                                                                            rows_all, 256, st.ld, st.Lpin, cnt);
+        int h = 0;
+        DSB_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+        DSB_CUDA(cudaStreamSynchronize(s));
+        fprintf(stderr, "[front check] %d mismatching elements of %lld\n", h, total);
+        cudaFree(cnt);
         break;
       }
       case ST_STEM: {

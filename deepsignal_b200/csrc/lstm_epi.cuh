@@ -1,0 +1,60 @@
+// lstm_epi.cuh — the LSTM cell update of one 64-gate-column group (16 hidden units) of one TMEM lane quadrant, shared by
+// the single-CTA and the CTA-pair sequence kernels.
+#pragma once
+#include "tc_common.cuh"
+
+namespace dsb {
+
+// t_addr: TMEM address of the group's first column for this warp's lane quadrant; cblk: this lane's first float4 of the
+// group's cell-state block (4 float4 per lane, 32 lanes apart); bias: smem bias of the group's first column.
+// 32 columns (8 hidden units) at a time keep the live registers < 96.  `release` is called once, right after the last
+// tcgen05.ld of the group has completed.
+template <bool F16, class Release>
+__device__ __forceinline__ void lstm_epi_group(uint32_t t_addr, float4* cblk, bool c_in, bool c_out, const float* bias,
+                                               uint32_t (&pk)[8], int ablate, Release&& release) {
+  using namespace tc;
+#pragma unroll
+  for (int sub = 0; sub < 2; ++sub) {
+    // the cell state is private to this CTA and was written one step (~20 us) ago: L2 hits
+    float4 cprev[2];
+    if (c_in) {
+      cprev[0] = cblk[(2 * sub) * 32];
+      cprev[1] = cblk[(2 * sub + 1) * 32];
+    } else {
+      cprev[0] = cprev[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t r[2][16];
+    __syncwarp();
+    tc_ld16(t_addr + (uint32_t)(32 * sub), r[0]);
+    tc_ld16(t_addr + (uint32_t)(32 * sub + 16), r[1]);
+    tc_wait_ld();
+    if (sub == 1) release();
+    float hn[8];
+#pragma unroll
+    for (int i2 = 0; i2 < 2; ++i2) {
+      const int i = 2 * sub + i2;
+      const float cpv[4] = {cprev[i2].x, cprev[i2].y, cprev[i2].z, cprev[i2].w};
+      float cn[4];
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + 16 * i + 4 * j);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + 16 * i + 4 * j + 4);
+        const float za[4] = {__uint_as_float(r[i2][4 * j + 0]) + b0.x, __uint_as_float(r[i2][4 * j + 1]) + b0.y,
+                             __uint_as_float(r[i2][4 * j + 2]) + b0.z, __uint_as_float(r[i2][4 * j + 3]) + b0.w};
+        const float zb[4] = {__uint_as_float(r[i2][4 * j + 4]) + b1.x, __uint_as_float(r[i2][4 * j + 5]) + b1.y,
+                             __uint_as_float(r[i2][4 * j + 6]) + b1.z, __uint_as_float(r[i2][4 * j + 7]) + b1.w};
+        if (ablate & 4) {
+          cn[j] = za[0] + za[1] + cpv[j]; cn[j + 1] = zb[0] + zb[1] + cpv[j + 1];
+          hn[4 * i2 + j] = za[2] + za[3]; hn[4 * i2 + j + 1] = zb[2] + zb[3];
+        } else {
+          lstm_unit_pair_fast(za, zb, cpv[j], cpv[j + 1], cn[j], cn[j + 1], hn[4 * i2 + j], hn[4 * i2 + j + 1]);
+        }
+      }
+      if (c_out) cblk[i * 32] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[4 * sub + i] = pack16<F16>(hn[2 * i], hn[2 * i + 1]);
+  }
+}
+
+}  // namespace dsb

@@ -20,6 +20,7 @@
 #include "lstm_seq.cuh"
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
+#include "lstm_epi.cuh"
 
 namespace dsb {
 namespace {
@@ -199,53 +200,12 @@ lstm_seq_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p,
           const int col = ch * SEQ_BN + c;
           float4* cblk = reinterpret_cast<float4*>(p.c[d]) + ((((size_t)mt * (GATES / 64) + (size_t)(col >> 6)) * 4 + q) * 4) * 32 + lane;
           uint32_t pk[8];
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {         // 32 columns (8 hidden units) at a time keeps the live registers < 96
-            // the cell state is private to this CTA and was written one step (~20 us) ago: L2 hits
-            float4 cprev[2];
-            if (c_in) {
-              cprev[0] = cblk[(2 * sub) * 32];
-              cprev[1] = cblk[(2 * sub + 1) * 32];
-            } else {
-              cprev[0] = cprev[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            uint32_t r[2][16];
+          lstm_epi_group<F16>(t_row + (uint32_t)c, cblk, c_in, c_out, sb + col, pk, ablate, [&]() {
+            // the accumulator stage is in registers now: hand it back to the MMA warp before doing the math
+            tc_fence_before();
             __syncwarp();
-            tc_ld16(t_row + (uint32_t)(c + 32 * sub), r[0]);
-            tc_ld16(t_row + (uint32_t)(c + 32 * sub + 16), r[1]);
-            tc_wait_ld();
-            if (g == GROUPS - 1 && sub == 1) {
-              // the accumulator stage is in registers now: hand it back to the MMA warp before doing the math
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tempty_bar(acc));
-            }
-            float hn[8];
-#pragma unroll
-            for (int i2 = 0; i2 < 2; ++i2) {
-              const int i = 2 * sub + i2;
-              const float cpv[4] = {cprev[i2].x, cprev[i2].y, cprev[i2].z, cprev[i2].w};
-              float cn[4];
-#pragma unroll
-              for (int j = 0; j < 4; j += 2) {
-                const float4 b0 = *reinterpret_cast<const float4*>(sb + col + 16 * i + 4 * j);
-                const float4 b1 = *reinterpret_cast<const float4*>(sb + col + 16 * i + 4 * j + 4);
-                const float za[4] = {__uint_as_float(r[i2][4 * j + 0]) + b0.x, __uint_as_float(r[i2][4 * j + 1]) + b0.y,
-                                     __uint_as_float(r[i2][4 * j + 2]) + b0.z, __uint_as_float(r[i2][4 * j + 3]) + b0.w};
-                const float zb[4] = {__uint_as_float(r[i2][4 * j + 4]) + b1.x, __uint_as_float(r[i2][4 * j + 5]) + b1.y,
-                                     __uint_as_float(r[i2][4 * j + 6]) + b1.z, __uint_as_float(r[i2][4 * j + 7]) + b1.w};
-                if (ablate & 4) {
-                  cn[j] = za[0] + za[1] + cpv[j]; cn[j + 1] = zb[0] + zb[1] + cpv[j + 1];
-                  hn[4 * i2 + j] = za[2] + za[3]; hn[4 * i2 + j + 1] = zb[2] + zb[3];
-                } else {
-                  lstm_unit_pair_fast(za, zb, cpv[j], cpv[j + 1], cn[j], cn[j + 1], hn[4 * i2 + j], hn[4 * i2 + j + 1]);
-                }
-              }
-              if (c_out) cblk[i * 32] = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) pk[4 * sub + i] = pack16<F16>(hn[2 * i], hn[2 * i + 1]);
-          }
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          });
           // h_t of this chunk: [128 x 64] tile in shared memory (128-byte rows, 16-byte pieces XOR-swizzled by row & 7 =
           // the SWIZZLE_128B pattern of the H tensor map) -> one TMA store of whole 128-byte lines
           if (et == 0 && store_pending && !(ablate & 16)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

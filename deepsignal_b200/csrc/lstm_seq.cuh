@@ -10,6 +10,7 @@ struct alignas(64) LstmSeqMaps {
   CUtensorMap f;                          // layer-0 feature rows F [KL*cap][FW], box 128 x 64
   CUtensorMap h[2][LSTM_SEQ_LAYERS];      // H[dir][layer] [(KL+1)*cap][256], box 128 x 64 (slot t+1 = output of step t)
   CUtensorMap w[2][LSTM_SEQ_LAYERS];      // gate weights [1024][Ktot] (columns 4*u+g), box 256 x 64
+  CUtensorMap w2[2][LSTM_SEQ_LAYERS];     // the same weights with a 128-row box (CTA-pair kernel: half a block per CTA)
 };
 
 struct LstmSeqParams {
@@ -29,5 +30,6 @@ struct LstmSeqLaunch {
 };
 
 void launch_lstm_seq(const LstmSeqLaunch& L, int n, int sm_count, cudaStream_t s);
+void launch_lstm_seq2(const LstmSeqLaunch& L, int n, int sm_count, cudaStream_t s);   // CTA-pair variant (lstm_seq2.cu)
 
 }  // namespace dsb

@@ -220,3 +220,21 @@ def test_persistent_lstm_kernel_matches_per_step_launches(engine, ckpt, precisio
     print("\n[lstm seq vs per-step, {}, n={}] max|dp|={:.3e} identical={}".format(precision, n, d, np.array_equal(a, b)))
     assert np.array_equal(a, b)
     assert np.array_equal(pa, pb)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("n", [3, 700])
+def test_fused_front_kernel_matches_separate_launches(engine, ckpt, precision, n, monkeypatch):
+    """front_tc.cu (conv1 + pool + conv2 + conv3 in one kernel) against stem_kernel + two GEMM launches: same
+    arithmetic and rounding points, so the probabilities must be bit-identical."""
+    x = _inputs(99, n)
+    monkeypatch.setenv("DSB_FRONT", "0")
+    engine.load_weights(ckpt)
+    a, pa = engine.forward(*x, precision=precision)
+    monkeypatch.setenv("DSB_FRONT", "1")
+    engine.load_weights(ckpt)
+    b, pb = engine.forward(*x, precision=precision)
+    d = np.abs(a - b).max()
+    print("\n[front fused vs separate, {}, n={}] max|dp|={:.3e} identical={}".format(precision, n, d, np.array_equal(a, b)))
+    assert np.array_equal(a, b)
+    assert np.array_equal(pa, pb)
