@@ -366,6 +366,12 @@ struct Builder {
               encode_map_16(&A.maps.x, X, rows_cap, cin, xld, 128, 64, f16);
               encode_map_16(&A.maps.wp1, Wp1.w, 192, Wp1.Ktot, Wp1.Ktot, 192, 64, f16);
               encode_map_16(&A.maps.wb1, Wb1.w, 48, Wb1.Ktot, Wb1.Ktot, 48, 64, f16);
+              encode_map_16(&A.maps.ys, Y, rows_cap, CH, YLD, 32, 32, f16);                // epilogue TMA stores
+              encode_map_16(&A.maps.p3s, TP3, rows_cap, 32, 32, 32, 32, f16);
+              encode_map_16(&A.maps.p4s, TP4, rows_cap, 32, 32, 32, 32, f16);
+              encode_map_16(&A.maps.p5s, TP5, rows_cap, 32, 32, 32, 32, f16);
+              encode_map_16(&A.maps.pss, TPS, rows_cap, 48, 48, 32, 32, f16);
+              for (int k = 0; k < 240; ++k) A.p.biasv[k] = ha[k];
               A.p.Lp = Lp; A.p.L = L; A.p.Y = Y; A.p.ldY = YLD; A.p.P3 = TP3; A.p.P4 = TP4; A.p.P5 = TP5; A.p.PS = TPS; A.p.bias = biasA;
               InceptBLaunch& B = sb.ib;
               B.fp16 = f16;
@@ -376,6 +382,8 @@ struct Builder {
               encode_map_16(&B.maps.w4, Wb4.w, 48, Wb4.Ktot, Wb4.Ktot, 48, 32, f16);
               encode_map_16(&B.maps.w5b, Wb5b.w, 64, Wb5b.Ktot, Wb5b.Ktot, 64, 32, f16);
               encode_map_16(&B.maps.w5c, Wb5c.w, 48, Wb5c.Ktot, Wb5c.Ktot, 48, 32, f16);
+              encode_map_16(&B.maps.ys, Y, rows_cap, CH, YLD, 32, 32, f16);               // epilogue TMA stores
+              for (int k = 0; k < 208; ++k) B.p.biasv[k] = hb[k];
               B.p.Lp = Lp; B.p.L = L; B.p.PS = TPS; B.p.Y = Y; B.p.ldY = YLD; B.p.bias = biasB;
             }
             plan.steps.push_back(sa);

@@ -64,7 +64,7 @@ struct ASmem {
 
 template <bool F16>
 __global__ void __launch_bounds__(A_THREADS, 1)
-incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p, const int num_tiles) {
+incept_a_kernel(const __grid_constant__ InceptAMaps maps, const __grid_constant__ InceptAParams p, const int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,7 +76,6 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
   auto tfull = [&](int a) { return base + ASmem::bars + 8u * (4 * A_SLOTS + 1 + a); };
   auto tempty = [&](int a) { return base + ASmem::bars + 8u * (4 * A_SLOTS + 3 + a); };
   const uint32_t tmem_slot = base + ASmem::tmem_slot;
-  float* sbias = reinterpret_cast<float*>(smem_raw + (base + ASmem::bias - smem_u32(smem_raw)));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < A_SLOTS; ++s) { mbar_init(full_x(s), 1); mbar_init(p1_done(s), 1); mbar_init(full_xp(s), 4); mbar_init(empty(s), 1); }
@@ -84,7 +83,6 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 240; i += A_THREADS) sbias[i] = p.bias[i];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -223,29 +221,25 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
       const bool row_ok = i >= 1 && i <= INCEPT_A_TILE_ROWS && row < p.M && !(p.ablate & 2);
       const uint32_t ok_mask = __ballot_sync(0xffffffffu, row_ok);
       const bool halo = (row % p.Lp) >= p.L;
-      // 32-column groups: g0..g2 -> Y[:, 0:96) (b1 | b2), g3/g4/g5 -> planes P3/P4/P5, g6 + g7 (16 wide) -> stem plane
+      // 32-column groups: g0..g2 -> Y[:, 0:96) (b1 | b2), g3/g4/g5 -> planes P3/P4/P5, g6 / g7 -> stem plane (g7 = stem
+      // channels 16..47, overlapping g6 by 16 so that every group is 32 wide).
+      // g0, g1 hold b1, whose first / last tile row lacks a pool neighbour: row-masked staged stores.  Everything from g2 on is a
+      // 1x1 conv of x and is valid on all 128 tile rows (the rows shared with the neighbouring tile get identical values),
+      // so those groups leave as one TMA store per warp: no shared-memory read-back by the threads.
       for (int g = half; g < 8; g += 2) {
-        const int c = g * 32;
-        const bool two = g < 7;
+        const int c = g < 7 ? g * 32 : 208;
         uint32_t rr[2][16];
         __syncwarp();
         tc_ld16(t_row + (uint32_t)c, rr[0]);
-        if (two) tc_ld16(t_row + (uint32_t)(c + 16), rr[1]);
+        tc_ld16(t_row + (uint32_t)(c + 16), rr[1]);
         tc_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-          if (h2 == 1 && !two) break;
           const int col = c + 16 * h2;
           float v[16];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 bb = *reinterpret_cast<const float4*>(sbias + col + 4 * k);
-            v[4 * k + 0] = __uint_as_float(rr[h2][4 * k + 0]) + bb.x;
-            v[4 * k + 1] = __uint_as_float(rr[h2][4 * k + 1]) + bb.y;
-            v[4 * k + 2] = __uint_as_float(rr[h2][4 * k + 2]) + bb.z;
-            v[4 * k + 3] = __uint_as_float(rr[h2][4 * k + 3]) + bb.w;
-          }
+          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(rr[h2][k]) + p.biasv[col + k];
           if (g < 6) {                                    // the residual stem (g6, g7) keeps its sign
 #pragma unroll
             for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
@@ -257,13 +251,31 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
 #pragma unroll
           for (int k = 0; k < 8; ++k) pk[8 * h2 + k] = pack16<F16>(v[2 * k], v[2 * k + 1]);
         }
-        uint8_t* dst;
-        size_t pitch;
-        if (g < 3) { pitch = (size_t)p.ldY * 2; dst = reinterpret_cast<uint8_t*>(p.Y) + (ptrdiff_t)wrow0 * (ptrdiff_t)pitch + g * 64; }
-        else if (g < 6) { pitch = 64; dst = reinterpret_cast<uint8_t*>(g == 3 ? p.P3 : g == 4 ? p.P4 : p.P5) + (ptrdiff_t)wrow0 * 64; }
-        else { pitch = 96; dst = reinterpret_cast<uint8_t*>(p.PS) + (ptrdiff_t)wrow0 * 96 + (g - 6) * 64; }
-        if (two) staged_store<4>(stage, pk, lane, ok_mask, dst, pitch);
-        else staged_store<2>(stage, pk, lane, ok_mask, dst, pitch);
+        // the staging tile may still be the source of this warp's previous TMA store
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        if (g < 2 || wrow0 < 0) {                         // (TMA stores reject negative coordinates: first warp of tile 0)
+          uint8_t* dst;
+          size_t pitch;
+          if (g < 3) { pitch = (size_t)p.ldY * 2; dst = reinterpret_cast<uint8_t*>(p.Y) + (ptrdiff_t)wrow0 * (ptrdiff_t)pitch + g * 64; }
+          else if (g < 6) { pitch = 64; dst = reinterpret_cast<uint8_t*>(g == 3 ? p.P3 : g == 4 ? p.P4 : p.P5) + (ptrdiff_t)wrow0 * 64; }
+          else { pitch = 96; dst = reinterpret_cast<uint8_t*>(p.PS) + (ptrdiff_t)wrow0 * 96 + (g == 7 ? 32 : 0); }
+          staged_store<4>(stage, pk, lane, ok_mask, dst, pitch);
+        } else {
+          const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc)
+            sts128(stage + (uint32_t)lane * 64u + (((uint32_t)pc ^ sw) << 4), make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]));
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(p.ablate & 2)) {
+            const CUtensorMap* mp = g == 2 ? &maps.ys : g == 3 ? &maps.p3s : g == 4 ? &maps.p4s : g == 5 ? &maps.p5s : &maps.pss;
+            const int col = g == 2 ? 64 : g == 7 ? 16 : 0;
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(mp)), "r"(stage), "r"(col), "r"(wrow0) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -271,6 +283,7 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // shared memory stays valid until every store has read it
   }
 
   tc_fence_before();
@@ -285,7 +298,7 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const InceptAParams p,
 // Kernel B
 // ============================================================================================
 constexpr int B_THREADS = 448;       // warp 0 TMA, warp 1 MMA, warps 2-5 branch-5 staging, warps 6-13 epilogue
-constexpr int B_SLOTS = 12;                            // ring of plane tiles, 3 per row tile
+constexpr int B_SLOTS = 10;                            // ring of plane tiles, 3 per row tile
 constexpr int B_TILE_ROWS = 136;                       // rows r0-2 .. r0+133 of one plane (taps reach r0-2 .. r0+129)
 constexpr uint32_t B_SLOT_BYTES = B_TILE_ROWS * 32 * 2; // one [136 x 32] SWIZZLE_64B tile = 8704 B (17 x 512)
 constexpr uint32_t B_U_BYTES = 128 * 32 * 2;            // one [128 x 32] k-block of the staged relu(b5b) tile
@@ -302,8 +315,8 @@ struct BSmem {
   static constexpr uint32_t w5c = w5b + 3 * B_W64_BLK;
   static constexpr uint32_t u = w5c + 2 * B_W48_BLK;          // 43008: 3 stages x two [128 x 32] blocks
   static constexpr uint32_t ring = u + 2 * B_ACC_STAGES * B_U_BYTES;
-  static constexpr uint32_t stage = ring + B_SLOTS * B_SLOT_BYTES;          // 8 epilogue warps x 2 KB
-  static constexpr uint32_t bars = stage + 8 * EPI_STAGE_BYTES;
+  static constexpr uint32_t stage = ring + B_SLOTS * B_SLOT_BYTES;          // 8 epilogue warps x 2 x 2 KB (TMA-store sources)
+  static constexpr uint32_t bars = stage + 16 * EPI_STAGE_BYTES;
   // barriers: full[S] empty[S] wbar b5b_full[3] u_full[3] tfull[3] tempty[3]
   static constexpr uint32_t nbars = 2 * B_SLOTS + 1 + 4 * B_ACC_STAGES;
   static constexpr uint32_t tmem_slot = (bars + 8 * nbars + 15u) & ~15u;
@@ -313,7 +326,7 @@ struct BSmem {
 
 template <bool F16>
 __global__ void __launch_bounds__(B_THREADS, 1)
-incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p, const int num_tiles) {
+incept_b_kernel(const __grid_constant__ InceptBMaps maps, const __grid_constant__ InceptBParams p, const int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -325,7 +338,6 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
   auto tfull = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + 2 * B_ACC_STAGES + a); };
   auto tempty = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + 3 * B_ACC_STAGES + a); };
   const uint32_t tmem_slot = base + BSmem::tmem_slot;
-  float* sbias = reinterpret_cast<float*>(smem_raw + (base + BSmem::bias - smem_u32(smem_raw)));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < B_SLOTS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
@@ -333,7 +345,6 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
     for (int a = 0; a < B_ACC_STAGES; ++a) { mbar_init(b5b_full(a), 1); mbar_init(u_full(a), 4); mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 208; i += B_THREADS) sbias[i] = p.bias[i];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -449,9 +460,8 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[4];
           const int e0 = kb * 32 + c * 8;                      // first b5b output channel of this 16-byte chunk
-          const float4 b0 = *reinterpret_cast<const float4*>(sbias + 144 + e0);
-          const float4 b1 = *reinterpret_cast<const float4*>(sbias + 144 + e0 + 4);
-          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const float bv[8] = {p.biasv[144 + e0], p.biasv[144 + e0 + 1], p.biasv[144 + e0 + 2], p.biasv[144 + e0 + 3],
+                               p.biasv[144 + e0 + 4], p.biasv[144 + e0 + 5], p.biasv[144 + e0 + 6], p.biasv[144 + e0 + 7]};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int e = e0 + 2 * k;
@@ -472,51 +482,46 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
   } else {
     // ---------------- epilogue warps: b3, b4, b5 = relu(stem + b5c) -> Y[:, 96:240] ----------------
     // accumulator column t (b3 [0,48) | b4 [48,96) | b5c [96,144)) is output channel 96 + t and bias index t.
+    // Five 32-column groups per row tile: t0 = 0, 32, 64, 96 and 112 (the last one overlaps the fourth by 16 columns so
+    // that every group is a full [32 rows x 32 columns] box).  A warp converts its 32 rows of a group, writes them as a
+    // SWIZZLE_64B tile into one of its two staging buffers and issues one TMA store: whole 64-byte row segments, no
+    // shared-memory read-back by the threads.  Rows >= M inside the tensor are written too (never consumed).
     const int q = warp & 3;
     const int half = (warp - 6) >> 2;
-    const uint32_t stage = base + BSmem::stage + (uint32_t)(warp - 6) * EPI_STAGE_BYTES;
+    const uint32_t stage = base + BSmem::stage + (uint32_t)(warp - 6) * 2u * EPI_STAGE_BYTES;
+    uint32_t stage_sel = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int i = q * 32 + lane;
       const int row = tile * 128 + i;
       const int wrow0 = tile * 128 + q * 32;
-      const bool row_ok = row < p.M && !(p.ablate & 2);
-      const uint32_t ok_mask = __ballot_sync(0xffffffffu, row_ok);
       const bool halo = (row % p.Lp) >= p.L;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * B_ACC_STRIDE;
       // the residual (stem plane) is an input: fetch it before waiting for the accumulators.
-      // warp set 1 owns group 3 (stem channels 0..31), warp set 0 owns group 4 (stem channels 32..47).
+      // warp set 1 owns group 3 (stem channels 0..31), warp set 0 owns group 4 (stem channels 16..47).
       uint4 res[4];
       {
         const uint4* tp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.PS) + (size_t)(row < p.M ? row : 0) * 48);
-        if (half == 1) { res[0] = __ldg(tp); res[1] = __ldg(tp + 1); res[2] = __ldg(tp + 2); res[3] = __ldg(tp + 3); }
-        else { res[0] = __ldg(tp + 4); res[1] = __ldg(tp + 5); res[2] = res[0]; res[3] = res[1]; }
+        const int o = half == 1 ? 0 : 2;
+        res[0] = __ldg(tp + o); res[1] = __ldg(tp + o + 1); res[2] = __ldg(tp + o + 2); res[3] = __ldg(tp + o + 3);
       }
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
       for (int g = half; g < 5; g += 2) {
-        const int t0 = g * 32;
-        const bool two = g < 4;
+        const int t0 = g < 4 ? g * 32 : 112;
         uint32_t rr[2][16];
         __syncwarp();
         tc_ld16(t_row + (uint32_t)t0, rr[0]);
-        if (two) tc_ld16(t_row + (uint32_t)(t0 + 16), rr[1]);
+        tc_ld16(t_row + (uint32_t)(t0 + 16), rr[1]);
         tc_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-          if (h2 == 1 && !two) break;
           const int t = t0 + 16 * h2;
           float v[16];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 bb = *reinterpret_cast<const float4*>(sbias + t + 4 * k);
-            v[4 * k + 0] = __uint_as_float(rr[h2][4 * k + 0]) + bb.x;
-            v[4 * k + 1] = __uint_as_float(rr[h2][4 * k + 1]) + bb.y;
-            v[4 * k + 2] = __uint_as_float(rr[h2][4 * k + 2]) + bb.z;
-            v[4 * k + 3] = __uint_as_float(rr[h2][4 * k + 3]) + bb.w;
-          }
+          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(rr[h2][k]) + p.biasv[t + k];
           if (g >= 3) {                                   // + stem
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -535,16 +540,29 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const InceptBParams p,
 #pragma unroll
           for (int k = 0; k < 8; ++k) pk[8 * h2 + k] = pack16<F16>(v[2 * k], v[2 * k + 1]);
         }
-        const size_t pitch = (size_t)p.ldY * 2;
-        uint8_t* dst = reinterpret_cast<uint8_t*>(p.Y) + (ptrdiff_t)wrow0 * (ptrdiff_t)pitch + (96 + t0) * 2;
-        if (two) staged_store<4>(stage, pk, lane, ok_mask, dst, pitch);
-        else staged_store<2>(stage, pk, lane, ok_mask, dst, pitch);
+        // the buffer about to be rewritten was the source of the store issued two groups ago
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t stg = stage + stage_sel * EPI_STAGE_BYTES;
+        const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc)
+          sts128(stg + (uint32_t)lane * 64u + (((uint32_t)pc ^ sw) << 4), make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && !(p.ablate & 2)) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&maps.ys)), "r"(stg), "r"(96 + t0), "r"(wrow0) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        stage_sel ^= 1u;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(acc));
       if (++acc == B_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // shared memory stays valid until every store has read it
   }
 
   tc_fence_before();

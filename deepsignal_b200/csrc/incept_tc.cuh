@@ -13,7 +13,7 @@
 
 namespace dsb {
 
-struct alignas(64) InceptAMaps { CUtensorMap x, wp1, wb1; };
+struct alignas(64) InceptAMaps { CUtensorMap x, wp1, wb1, ys, p3s, p4s, p5s, pss; };   // *s: [32 x 32] store boxes over Y and the planes
 struct InceptAParams {
   int M = 0, Lp = 0, L = 0;
   int nkb = 4;                 // 64-wide K blocks of the input channels (256 or 240 -> 4)
@@ -22,16 +22,18 @@ struct InceptAParams {
   void* PS = nullptr;                                           // [M][48] plane: residual stem
   int ablate = 0;              // timing experiments only (DSB_ABLATE_A): 1 skip pool math, 2 skip epilogue stores
   const float* bias = nullptr; // [240]: b1 (48) then p1 (b2 48 | b3a 32 | b4a 32 | b5a 32 | stem 48)
+  float biasv[240];            // the same values by value: read through the constant bank (LDC), not shared memory
 };
 struct InceptALaunch { InceptAMaps maps; InceptAParams p; bool fp16 = false; };
 
-struct alignas(64) InceptBMaps { CUtensorMap t3, t4, t5, w3, w4, w5b, w5c; };
+struct alignas(64) InceptBMaps { CUtensorMap t3, t4, t5, w3, w4, w5b, w5c, ys; };   // ys: Y as [32 x 32] store boxes
 struct InceptBParams {
   int M = 0, Lp = 0, L = 0;
   const void* PS = nullptr;    // [M][48] residual stem plane
   void* Y = nullptr; int ldY = 0;
   int ablate = 0;              // timing experiments only (DSB_ABLATE_B): 1 skip staging math, 2 skip epilogue stores
   const float* bias = nullptr; // [208]: b3 48 | b4 48 | b5c 48 | b5b 64
+  float biasv[208];            // by value: constant-bank reads keep the bias off the shared-memory data pipe
 };
 struct InceptBLaunch { InceptBMaps maps; InceptBParams p; bool fp16 = false; };
 
