@@ -9,17 +9,34 @@ namespace dsb {
 // group's cell-state block (4 float4 per lane, 32 lanes apart); bias: smem bias of the group's first column.
 // 32 columns (8 hidden units) at a time keep the live registers < 96.  `release` is called once, right after the last
 // tcgen05.ld of the group has completed.
+// The cell state is re-read by the same CTA one step later: keep its lines in L2 (evict_last) while the H slots and
+// weights stream through.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_c(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_c(float4* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 template <bool F16, class Release>
 __device__ __forceinline__ void lstm_epi_group(uint32_t t_addr, float4* cblk, bool c_in, bool c_out, const float* bias,
                                                uint32_t (&pk)[8], int ablate, Release&& release) {
   using namespace tc;
+  const uint64_t pol = l2_policy_evict_last();
 #pragma unroll
   for (int sub = 0; sub < 2; ++sub) {
     // the cell state is private to this CTA and was written one step (~20 us) ago: L2 hits
     float4 cprev[2];
     if (c_in) {
-      cprev[0] = cblk[(2 * sub) * 32];
-      cprev[1] = cblk[(2 * sub + 1) * 32];
+      cprev[0] = ld_c(cblk + (2 * sub) * 32, pol);
+      cprev[1] = ld_c(cblk + (2 * sub + 1) * 32, pol);
     } else {
       cprev[0] = cprev[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -50,7 +67,7 @@ __device__ __forceinline__ void lstm_epi_group(uint32_t t_addr, float4* cblk, bo
           lstm_unit_pair_fast(za, zb, cpv[j], cpv[j + 1], cn[j], cn[j + 1], hn[4 * i2 + j], hn[4 * i2 + j + 1]);
         }
       }
-      if (c_out) cblk[i * 32] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      if (c_out) st_c(cblk + i * 32, make_float4(cn[0], cn[1], cn[2], cn[3]), pol);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) pk[4 * sub + i] = pack16<F16>(hn[2 * i], hn[2 * i + 1]);
