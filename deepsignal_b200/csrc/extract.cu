@@ -20,7 +20,7 @@ namespace dsb {
 
 struct ExtractWork {
   DevBuf base_mean, base_std, base_len, counts, offsets, shift, scale, scratch, total, tmp_read, tmp_loc;
-  DevBuf vmin, bins, lut_off, lut;
+  DevBuf vmin, bins, lut_off, lut, need;
 };
 void destroy_extract(ExtractWork* p) { delete p; }
 
@@ -276,6 +276,7 @@ struct BaseParams {
   const int32_t* ev_start; const int32_t* ev_len; const int64_t* ev_off; int64_t R; int64_t total_ev;
   const double* lut; const int64_t* lut_off; const int32_t* vmin;
   double* base_mean; double* base_std; int32_t* base_len;
+  const uint8_t* need;       // per base: 1 if some targeted site's k-mer covers it (others are never read downstream)
 };
 
 struct NormAt {
@@ -289,7 +290,7 @@ struct SqDevAt {
 
 __global__ void base_stats_kernel(const BaseParams p) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= p.total_ev) return;
+  if (e >= p.total_ev || !p.need[e]) return;
   const int r = find_read(p.ev_off, p.R, e);
   const int64_t N = p.raw_off[r + 1] - p.raw_off[r];
   // python slice norm[s : s+l] for s >= 0 (negative starts are rejected on the host side)
@@ -306,6 +307,17 @@ __global__ void base_stats_kernel(const BaseParams p) {
   const double var = __ddiv_rn(pairwise_sum(g, 0, n), (double)n);
   p.base_mean[e] = mean;
   p.base_std[e] = sqrt(var);
+}
+
+// Only the bases inside some targeted site's k-mer are read by site_feature_kernel: flag them so that base_stats_kernel
+// skips the rest (CpG sites are ~1 % of the bases; whole warps of unflagged bases exit at once).
+__global__ void mark_need_kernel(const int32_t* __restrict__ site_read, const int32_t* __restrict__ site_loc, const int64_t* __restrict__ ev_off,
+                                 int64_t n_sites, int klen, uint8_t* __restrict__ need) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sites * klen) return;
+  const int64_t sidx = i / klen;
+  const int k = (int)(i - sidx * klen);
+  need[ev_off[site_read[sidx]] + site_loc[sidx] - (klen - 1) / 2 + k] = 1;
 }
 
 struct MotifSet { int n, len, mod_loc, nbh; char seq[512]; };
@@ -563,14 +575,6 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
     DSB_CUDA(cudaGetLastError());
     ctx->launches++;
   }
-  if (total_ev > 0) {
-    BaseParams bp{rd->raw, rd->raw_off, rd->ev_start, rd->ev_len, rd->ev_off, R, total_ev,
-                  w.lut.as<double>(), w.lut_off.as<int64_t>(), w.vmin.as<int32_t>(),
-                  w.base_mean.as<double>(), w.base_std.as<double>(), w.base_len.as<int32_t>()};
-    base_stats_kernel<<<(unsigned)((total_ev + 127) / 128), 128, 0, s>>>(bp);
-    DSB_CUDA(cudaGetLastError());
-    ctx->launches++;
-  }
   const int64_t emit = std::min<int64_t>(total, sites->capacity);
   if (read_shift) DSB_CUDA(cudaMemcpyAsync(read_shift, w.shift.p, R * sizeof(double), cudaMemcpyDeviceToDevice, s));
   if (read_scale) DSB_CUDA(cudaMemcpyAsync(read_scale, w.scale.p, R * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -586,6 +590,19 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
     }
     site_emit_kernel<<<grid_r, 128, 0, s>>>(rd->ev_base, rd->ev_off, R, ms, w.offsets.as<int64_t>(), emit, sr, sl);
     DSB_CUDA(cudaGetLastError());
+    if (total_ev > 0) {
+      w.need.ensure((size_t)total_ev);
+      DSB_CUDA(cudaMemsetAsync(w.need.p, 0, (size_t)total_ev, s));
+      const int64_t marks = emit * prm->kmer_len;
+      mark_need_kernel<<<(unsigned)((marks + 255) / 256), 256, 0, s>>>(sr, sl, rd->ev_off, emit, prm->kmer_len, w.need.as<uint8_t>());
+      DSB_CUDA(cudaGetLastError());
+      BaseParams bp{rd->raw, rd->raw_off, rd->ev_start, rd->ev_len, rd->ev_off, R, total_ev,
+                    w.lut.as<double>(), w.lut_off.as<int64_t>(), w.vmin.as<int32_t>(),
+                    w.base_mean.as<double>(), w.base_std.as<double>(), w.base_len.as<int32_t>(), w.need.as<uint8_t>()};
+      base_stats_kernel<<<(unsigned)((total_ev + 127) / 128), 128, 0, s>>>(bp);
+      DSB_CUDA(cudaGetLastError());
+      ctx->launches += 2;
+    }
     SiteParams sp;
     sp.rd = *rd;
     sp.lut = w.lut.as<double>(); sp.lut_off = w.lut_off.as<int64_t>(); sp.vmin = w.vmin.as<int32_t>();
