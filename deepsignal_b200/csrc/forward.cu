@@ -37,6 +37,7 @@ struct Step {
   InceptBLaunch ib;
   LstmSeqLaunch seq;
   FrontLaunch front;
+  bool front_cc = false;      // DSB_FRONT=1: CUDA-core stem (front_tc.cu, bit-identical to the separate launches) instead of front2_tc.cu
   int epi_kind = EPI_CONV;
   int kclass = KC_GEMM;
   double flops_per_row = 0;
@@ -274,11 +275,13 @@ struct Builder {
         const char* ev = getenv("DSB_FRONT");        // DSB_FRONT=0 keeps stem_kernel + two GEMM launches (A/B tests)
         front = !(ev && ev[0] == '0');
       }
+      T* wB1 = reinterpret_cast<T*>(wa.take((size_t)192 * 64 * sizeof(T)));
       if (front) {
         if constexpr (TC) {
           // conv1 + pool + conv2 + conv3 in one kernel (front_tc.cu): P1 and C2 stay in shared memory
           Step st;
           st.kind = ST_FRONT;
+          { const char* ev = getenv("DSB_FRONT"); st.front_cc = ev && ev[0] == '1'; }
           st.stream = 0;
           st.rows_per_sample = Lp2;
           st.kclass = KC_GEMM;
@@ -293,6 +296,24 @@ struct Builder {
             Q.p.S = S; Q.p.w1 = w1; Q.p.b1 = b1; Q.p.b2 = Wc2.bias; Q.p.b3 = Wc3.bias;
             Q.p.L1 = fm.L1; Q.p.L = L2; Q.p.Lp = Lp2; Q.p.conv_pl = conv_total / 2; Q.p.pool_pl = pool_total / 2;
             Q.p.X0 = X0; Q.p.ldX = 256;
+            // front2: conv1 as a 16-bit (hi | hi | lo) x (hi | lo | hi) MMA -- weights of channel c shifted to pool tap a in row a*64+c
+            std::vector<__half> hB1((size_t)192 * 64, __float2half_rn(0.f));     // fp16 parts in both precision modes
+            for (int a = 0; a < 3; ++a)
+              for (int c = 0; c < 64; ++c)
+                for (int t = 0; t < 7; ++t) {
+                  const float wf = fm.conv1.w[(size_t)c * 7 + t];
+                  const __half wh = __float2half_rn(wf);
+                  const __half wl = __float2half_rn(wf - __half2float(wh));
+                  const size_t row = (size_t)(a * 64 + c) * 64;
+                  const int k = 2 * a + t;
+                  hB1[row + k] = wh; hB1[row + 11 + k] = wh; hB1[row + 22 + k] = wl;
+                }
+            DSB_CUDA(cudaMemcpyAsync(wB1, hB1.data(), hB1.size() * sizeof(__half), cudaMemcpyHostToDevice, up_stream));
+            DSB_CUDA(cudaStreamSynchronize(up_stream));
+            encode_map_16(&Q.maps.w1, wB1, 192, 64, 64, 192, 64, true);
+            for (int k = 0; k < 64; ++k) Q.p.b1v[k] = fm.conv1.bias[k];
+            for (int k = 0; k < 128; ++k) Q.p.b2v[k] = fm.conv2.bias[k];
+            for (int k = 0; k < 256; ++k) Q.p.b3v[k] = fm.conv3.bias[k];
           }
           plan.steps.push_back(st);
         }
@@ -684,7 +705,8 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_FRONT: {
         if constexpr (!std::is_same<T, float>::value) {
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
-          launch_front(st.front, signals, (int)n, sms[st.stream], s);
+          if (st.front_cc) launch_front(st.front, signals, (int)n, sms[st.stream], s);
+          else launch_front2(st.front, signals, (int)n, sms[st.stream], s);
           ctx->launches++;
         }
         break;

@@ -12,6 +12,7 @@ namespace dsb {
 struct alignas(64) FrontMaps {
   CUtensorMap w2;     // conv2 weights [128][64], box 128 x 64
   CUtensorMap w3;     // conv3 weights [256][384] (K = tap*128 + channel), box 128 x 32
+  CUtensorMap w1;     // front2: conv1 (hi | hi | lo) parts [192][64], box 192 x 64
 };
 
 struct FrontParams {
@@ -25,6 +26,7 @@ struct FrontParams {
   int conv_pl = 0, pool_pl = 0;     // SAME-padding left pads
   void* X0 = nullptr; int ldX = 0;  // [n*Lp][ldX]
   int M = 0;                        // n * Lp
+  float b1v[64]; float b2v[128]; float b3v[256];   // front2: biases by value (constant bank)
 };
 
 struct FrontLaunch { FrontMaps maps; FrontParams p; bool fp16 = false; };
@@ -32,5 +34,6 @@ struct FrontLaunch { FrontMaps maps; FrontParams p; bool fp16 = false; };
 constexpr int FRONT_TILE_ROWS = 126;   // 128-row tiles overlap by one row on each side (conv3 halo)
 
 void launch_front(const FrontLaunch& L, const float* signals, int n, int sm_count, cudaStream_t s);
+void launch_front2(const FrontLaunch& L, const float* signals, int n, int sm_count, cudaStream_t s);   // conv1 on the tensor cores too (front2_tc.cu)
 
 }  // namespace dsb

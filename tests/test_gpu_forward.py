@@ -238,3 +238,16 @@ def test_fused_front_kernel_matches_separate_launches(engine, ckpt, precision, n
     print("\n[front fused vs separate, {}, n={}] max|dp|={:.3e} identical={}".format(precision, n, d, np.array_equal(a, b)))
     assert np.array_equal(a, b)
     assert np.array_equal(pa, pb)
+    # default front end (front2_tc.cu): conv1 on the tensor cores as split fp16 parts -- ~2^-22 relative on conv1 BEFORE
+    # the 16-bit rounding of its output, i.e. about 1e-4 of the P1 elements round to the neighbouring 16-bit value.  On the
+    # spread-logit checkpoint one such flip moves a probability by up to a few 1e-3 in bf16 mode (the same sensitivity
+    # that makes bf16-vs-oracle 1.5e-2 there: a flipped element re-draws the rounding noise of every later layer), so this
+    # is a statistical-equivalence check against the documented stress bounds, not bit-identity; the oracle tests above run
+    # on this default path and their error statistics are unchanged (bf16 1.466e-2 / fp16 1.985e-3 on the 2048-sample case).
+    monkeypatch.delenv("DSB_FRONT")
+    engine.load_weights(ckpt)
+    c, pc = engine.forward(*x, precision=precision)
+    d2 = np.abs(a - c).max()
+    print("[front2 (tensor-core conv1) vs separate, {}, n={}] max|dp|={:.3e} flips={}".format(precision, n, d2, int((pa != pc).sum())))
+    assert d2 <= (BF16_STRESS_BOUND if precision == "bf16" else FP16_STRESS_BOUND)
+    assert (pa != pc).mean() <= 0.02
