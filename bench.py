@@ -28,6 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+ALG_BYTES_INCEPT_A = 90 * (512 + 480) + 2 * 90 * 960 + 5 * 45 * 960 + 3 * 23 * 960   # 544,320 B per sample, see roofline below
 FLOP_PER_SAMPLE = 198.61e6          # executed MACs*2 after the exact folds
 BYTES_IN_PER_SAMPLE = 17 * 4 * 4 + 360 * 4   # 1712
 BYTES_OUT_PER_SAMPLE = 12
@@ -303,22 +304,39 @@ def main():
     torch.cuda.synchronize(dev)
     prof = eng.profile()
     eng.set_profiling(False)
-    tc_ms = prof["gemm"]["ms"] + prof["lstm_gemm"]["ms"]
-    tc_flops = prof["gemm"]["flops"] + prof["lstm_gemm"]["flops"]
-    tc_launches = prof["gemm"]["launches"] + prof["lstm_gemm"]["launches"]
-    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    peak = pk["bf16_tflops_sustained"]
-    traffic = None
+    tc = [prof[k] for k in ("gemm", "lstm_gemm", "incept_a")]
+    tc_ms = sum(v["ms"] for v in tc)
+    tc_flops = sum(v["flops"] for v in tc)
+    tc_launches = sum(v["launches"] for v in tc)
+    traffic_a, traffic_tc = None, None
     tp = os.path.join(ROOT, "profiles", "r1_traffic.json")      # ncu dram__bytes_{read,write}.sum of the same command, per launch
     if os.path.exists(tp):
         with open(tp) as fh:
-            traffic = json.load(fh).get("tensor_core_dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu, bytes per tensor-core launch, 32768-sample chunk)", "kernel": "gemm_tc_kernel (tcgen05 GEMM + fused conv/LSTM epilogue)",
-                "launches_profiled": tc_launches, "avg_launch_ms": tc_ms / max(tc_launches, 1),
-                "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+            tj = json.load(fh)
+        ka = [v for k, v in tj.get("kernels", {}).items() if k.startswith("incept_a_kernel")]
+        if ka:
+            traffic_a = ka[0]["dram_MB"] * 1e6 / ka[0]["launches"] * (n / tj["chunk_samples"] if n < tj["chunk_samples"] else 1.0)
+        traffic_tc = tj.get("tensor_core_dram_bytes_per_launch")
+    # dominant kernel = incept_a_kernel (11 launches per chunk, ~35 % of the step): HBM-bound.  Algorithmic bytes per sample
+    # (DESIGN.md section 4): sum over the 11 blocks of L_b real rows x (2*cin_b in + 480 out) = 544,320 B.
+    a_prof = prof["incept_a"]
+    a_bytes = ALG_BYTES_INCEPT_A * n
+    a_ach = a_bytes / (a_prof["ms"] * 1e-3) / 1e9 if a_prof["ms"] > 0 else 0.0
+    chunks = -(-n // a.max_chunk)
+    roofline = {"bound": "hbm", "achieved": a_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a_ach / pk["hbm_gbs"],
+                "traffic": traffic_a, "traffic_source": "profiles/r1_traffic.json (ncu dram bytes per incept_a_kernel launch, one 37888-sample chunk; algorithmic: %.0f)" % (a_bytes / max(a_prof["launches"], 1)),
+                "kernel": "incept_a_kernel (inception block, first half: 1x1 convs + in-SM max pool; 11 launches per chunk)",
+                "launches_profiled": a_prof["launches"], "avg_launch_ms": a_prof["ms"] / max(a_prof["launches"], 1),
+                "share_of_step": a_prof["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
+                "peak_source": pk["source"] + ", STREAM-style copy",
                 "breakdown_ms": {k: v["ms"] for k, v in prof.items()},
-                "whole_step_frac_of_peak": value / world * FLOP_PER_SAMPLE / 1e12 / peak}
+                # all tensor-core kernels together (front end, inception A/B, LSTM) against the tensor roofline
+                "tensor": {"achieved": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                           "frac": (tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0) / pk["bf16_tflops_sustained"],
+                           "launches_profiled": tc_launches, "traffic": traffic_tc,
+                           "peak_source": "sustained bf16 figure (kernels timed inside a long step)"},
+                "whole_step_frac_of_tensor_peak": value / world * FLOP_PER_SAMPLE / 1e12 / pk["bf16_tflops_sustained"],
+                "chunks_per_step": chunks}
 
     # ---- end to end through the host entry point (pinned host buffers, copies inside the timed region)
     ne = a.e2e_samples

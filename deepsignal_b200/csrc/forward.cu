@@ -369,7 +369,7 @@ struct Builder {
             float* biasA = reinterpret_cast<float*>(wa.take(240 * sizeof(float)));
             float* biasB = reinterpret_cast<float*>(wa.take(208 * sizeof(float)));
             Step sa, sb;
-            sa.kind = ST_INCEPT_A; sa.stream = 0; sa.rows_per_sample = Lp; sa.kclass = KC_GEMM;
+            sa.kind = ST_INCEPT_A; sa.stream = 0; sa.rows_per_sample = Lp; sa.kclass = KC_INCEPT_A;
             sb.kind = ST_INCEPT_B; sb.stream = 0; sb.rows_per_sample = Lp; sb.kclass = KC_GEMM;
             sa.flops_per_row = 2.0 * (double)cin * 240.0 * (double)L / (double)Lp;
             sb.flops_per_row = 2.0 * (96.0 * 48 + 160.0 * 48 + 96.0 * 64 + 64.0 * 48) * (double)L / (double)Lp;

@@ -42,7 +42,7 @@ struct GSmem {
   static constexpr uint32_t c2 = p1 + G_P1_BYTES;                    // 4 k-blocks
   static constexpr uint32_t stage = c2 + 4 * G_C2_KB;                // 8 epilogue warps x 2 KB
   static constexpr uint32_t bars = stage + 8 * EPI_STAGE_BYTES;
-  static constexpr uint32_t nbars = 1 + 12;
+  static constexpr uint32_t nbars = 1 + 18;
   static constexpr uint32_t tmem_slot = (bars + 8 * nbars + 15u) & ~15u;
   static constexpr uint32_t total = tmem_slot + 16;
 };
@@ -67,7 +67,9 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t wbar = base + GSmem::bars;
-  enum { A1_FULL = 0, A1_EMPTY, ACC1_FULL, ACC1_EMPTY, P1_FULL, P1_EMPTY, ACC2_FULL, ACC2_EMPTY, C2_FULL, C2_EMPTY, ACC3_FULL, ACC3_EMPTY };
+  // C2_FULL / C2_EMPTY exist per 32-channel k-block of the C2 tile: conv3 starts on k-block 0 while the staging warps
+  // still convert k-blocks 1..3, and the next tile's staging re-uses a k-block as soon as its three tap MMAs are done
+  enum { A1_FULL = 0, A1_EMPTY, ACC1_FULL, ACC1_EMPTY, P1_FULL, P1_EMPTY, ACC2_FULL, ACC2_EMPTY, ACC3_FULL, ACC3_EMPTY, C2_FULL, C2_EMPTY = C2_FULL + 4 };
   auto bar = [&](int kind) { return base + GSmem::bars + 8u * (1 + kind); };
   const uint32_t tmem_slot = base + GSmem::tmem_slot;
 
@@ -81,7 +83,7 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
     mbar_init(bar(ACC1_FULL), 1); mbar_init(bar(ACC1_EMPTY), 4);
     mbar_init(bar(P1_FULL), 4);   mbar_init(bar(P1_EMPTY), 1);
     mbar_init(bar(ACC2_FULL), 1); mbar_init(bar(ACC2_EMPTY), 4);
-    mbar_init(bar(C2_FULL), 4);   mbar_init(bar(C2_EMPTY), 1);
+    for (int kb = 0; kb < 4; ++kb) { mbar_init(bar(C2_FULL + kb), 4); mbar_init(bar(C2_EMPTY + kb), 1); }
     mbar_init(bar(ACC3_FULL), 1); mbar_init(bar(ACC3_EMPTY), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -138,17 +140,18 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
       auto mma3 = [&](int k) {
         const uint32_t ph = (uint32_t)k & 1u;
         mbar_wait(bar(ACC3_EMPTY), ph ^ 1u);
-        mbar_wait(bar(C2_FULL), ph);
-        tc_fence_after();
-        for (int tap = 0; tap < 3; ++tap)
-          for (int kb = 0; kb < 4; ++kb) {
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(bar(C2_FULL + kb), ph);
+          tc_fence_after();
+          for (int tap = 0; tap < 3; ++tap) {
             // output row i, tap t reads C2 row i + t - 1 = tile row i + t (the staging warps store one row down)
             const uint64_t ad = make_kmajor_desc<32>(base + GSmem::c2 + kb * G_C2_KB + (uint32_t)tap * 64u);
             const uint64_t bd = make_kmajor_desc<32>(base + GSmem::w3 + (tap * 4 + kb) * G_W3_BLK);
 #pragma unroll
             for (int j = 0; j < 2; ++j) tc_mma_bf16(tmem_base + ACC3, ad + 2 * j, bd + 2 * j, id128, (tap | kb | j) != 0 ? 1u : 0u);
           }
-        tc_commit(bar(C2_EMPTY));
+          tc_commit(bar(C2_EMPTY + kb));
+        }
         tc_commit(bar(ACC3_FULL));
       };
       for (int it = 0; it < my_tiles + 2; ++it) {
@@ -256,7 +259,6 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
       const bool zero = row < 0 || row >= p.M || (row % p.Lp) >= p.L;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + ACC2;
       mbar_wait(bar(ACC2_FULL), ph);
-      mbar_wait(bar(C2_EMPTY), ph ^ 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int kb = 0; kb < 4; ++kb) {
@@ -264,6 +266,12 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
         tc_ld16(t_row + (uint32_t)(kb * 32), r2[0]);
         tc_ld16(t_row + (uint32_t)(kb * 32 + 16), r2[1]);
         tc_wait_ld();
+        if (kb == 3) {                                       // conv2's accumulator is in registers: conv2 of the next tile may start
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(ACC2_EMPTY));
+        }
+        mbar_wait(bar(C2_EMPTY + kb), ph ^ 1u);
         const uint32_t ub = base + GSmem::c2 + kb * G_C2_KB + rr * 64u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -278,11 +286,10 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
           }
           sts128(ub + (((uint32_t)c ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
         }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(C2_FULL + kb));
       }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(bar(C2_FULL)); mbar_arrive(bar(ACC2_EMPTY)); }
     }
   } else {
     // ---------------- epilogue warps: relu(conv3 + bias) -> X0 ----------------

@@ -134,7 +134,7 @@ class Engine(object):
 
     def profile(self):
         out = {}
-        for cls, name in enumerate(("gemm", "lstm_gemm", "elementwise")):
+        for cls, name in enumerate(("gemm", "lstm_gemm", "elementwise", "incept_a")):
             ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
             self._check(self.lib.dsb_get_profile(self.h, cls, C.byref(ms), C.byref(n), C.byref(fl)))
             out[name] = dict(ms=ms.value, launches=n.value, flops=fl.value)

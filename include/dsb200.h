@@ -109,7 +109,8 @@ DSB_API int dsb_forward_host(dsb_ctx* ctx, int32_t precision, int64_t n,
                      const float* signals, float* probs, int32_t* pred);
 
 /* Per-kernel-class timing of the most recent profiled forward (CUDA events on the launch
- * stream around every launch of the class).  classes: 0 gemm, 1 lstm-gemm, 2 elementwise. */
+ * stream around every launch of the class).  classes: 0 tensor-core GEMM kernels other than 1 and 3,
+ * 1 LSTM kernel(s), 2 elementwise helpers, 3 inception kernel A (the largest share of a step). */
 DSB_API int dsb_set_profiling(dsb_ctx* ctx, int32_t enabled);
 DSB_API int dsb_get_profile(dsb_ctx* ctx, int32_t cls, double* ms_total, int64_t* launches, double* flops);
 DSB_API int64_t dsb_launch_count(const dsb_ctx* ctx);   /* kernels launched by this ctx so far */
