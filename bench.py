@@ -177,7 +177,7 @@ def bench_reads(a, eng, torch, dev, rank, world, barrier, max_over_ranks, ckpt):
                            "traffic": None, "kernel": "extraction kernel chain (5 launches per batch)",
                            "peak_source": pk["source"]}
         if rank == 0 and not a.no_cpu_baseline:
-            k = min(rb.n_reads, 40)
+            k = min(rb.n_reads, 1500)          # ~10 s of single-core NumPy work
             t0 = time.perf_counter()
             ns = 0
             for i in range(k):
