@@ -37,6 +37,7 @@ struct Step {
   InceptBLaunch ib;
   LstmSeqLaunch seq;
   FrontLaunch front;
+  bool lstm_pair = true;      // DSB_LSTM_PAIR=0: single-CTA sequence kernel (lstm_seq.cu) instead of the CTA-pair one (lstm_seq2.cu)
   bool front_cc = false;      // DSB_FRONT=1: CUDA-core stem (front_tc.cu, bit-identical to the separate launches) instead of front2_tc.cu
   int epi_kind = EPI_CONV;
   int kclass = KC_GEMM;
@@ -494,6 +495,7 @@ struct Builder {
           // one persistent kernel for all directions, layers and time steps of the chunk (lstm_seq.cu)
           Step st;
           st.kind = ST_LSTM_SEQ;
+          { const char* ev = getenv("DSB_LSTM_PAIR"); st.lstm_pair = !(ev && ev[0] == '0'); }
           st.stream = 1;
           st.rows_per_sample = 1;
           st.kclass = KC_LSTM;
@@ -695,8 +697,7 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_LSTM_SEQ: {
         if constexpr (!std::is_same<T, float>::value) {
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
-          static const bool lstm_pair = getenv("DSB_LSTM_PAIR") && getenv("DSB_LSTM_PAIR")[0] == '1';
-          if (lstm_pair) launch_lstm_seq2(st.seq, (int)n, sms[st.stream], s);
+          if (st.lstm_pair) launch_lstm_seq2(st.seq, (int)n, sms[st.stream], s);
           else launch_lstm_seq(st.seq, (int)n, sms[st.stream], s);
           ctx->launches++;
         }

@@ -36,7 +36,8 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // .relaxed: a .release.cluster arrive from the TMA-producer thread drains its outstanding bulk loads (profiles/experiments/pair_ring.cu)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
   asm volatile(

@@ -23,12 +23,12 @@ namespace {
 using namespace tc;
 
 constexpr int P_EW = 16;                                  // epilogue warps
-constexpr int P_THREADS = 64 + 32 * P_EW;
-constexpr int P_STAGES = 6;
+constexpr int P_THREADS = 64 + 32 * P_EW + 32;     // + one warp that issues the h_t TMA stores
+constexpr int P_STAGES = 5;
 constexpr uint32_t P_A_BYTES = 128 * 64 * 2, P_B_BYTES = 128 * 64 * 2, P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
 constexpr uint32_t P_HTILE_BYTES = 128 * 64 * 2;
 constexpr int P_CHUNKS = GATES / 256;
-constexpr size_t P_SMEM = 1024 + (size_t)P_STAGES * P_STAGE_BYTES + P_HTILE_BYTES + 256 + 2 * GATES * sizeof(float);
+constexpr size_t P_SMEM = 1024 + (size_t)P_STAGES * P_STAGE_BYTES + 2 * P_HTILE_BYTES + 256 + 2 * GATES * sizeof(float);
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -44,8 +44,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
   return r;
 }
+// Remote arrives are .relaxed: they carry no data (TMA bytes are tracked by complete_tx, TMEM reads are complete before the
+// arrive is issued).  A .release.cluster arrive issued by the TMA-producer thread drains that thread's outstanding bulk
+// loads and collapses the ring to depth 1 -- 1340 instead of 512 cycles per k-block (profiles/experiments/pair_ring.cu).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
@@ -95,18 +98,23 @@ lstm_seq2_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p
   const bool leader = rank == 0;
   const uint32_t ring_base = smem_base;
   const uint32_t htile = ring_base + P_STAGES * P_STAGE_BYTES;
-  const uint32_t bar_base = htile + P_HTILE_BYTES;
+  const uint32_t bar_base = htile + 2 * P_HTILE_BYTES;            // two h tiles: one being stored while the next is written
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (P_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * P_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * P_STAGES + 2 + a); };
   auto hready_bar = [&](int s) { return bar_base + 8u * (2 * P_STAGES + 4 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * P_STAGES + 6);
+  auto hfull_bar = [&](int b) { return bar_base + 8u * (2 * P_STAGES + 6 + b); };
+  auto hfree_bar = [&](int b) { return bar_base + 8u * (2 * P_STAGES + 8 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * P_STAGES + 10);
   float* sbias = reinterpret_cast<float*>(smem_raw + ((bar_base + 256u) - smem_u32(smem_raw)));     // [2 slots][1024]
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * P_EW); mbar_init(hready_bar(a), 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * P_EW); mbar_init(hready_bar(a), 1);
+      mbar_init(hfull_bar(a), P_EW); mbar_init(hfree_bar(a), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -193,7 +201,7 @@ lstm_seq2_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p
         }
       });
     }
-  } else {
+  } else if (warp < 2 + P_EW) {
     // ================= epilogue warps (both CTAs) =================
     const int q = warp & 3;
     const int cs = (warp - 2) >> 2;           // 64-column group of every 256-column chunk
@@ -202,7 +210,7 @@ lstm_seq2_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p
     int acc = 0;
     uint32_t acc_phase = 0;
     int bias_cp = -1, bias_layer = -1;
-    bool store_pending = false;
+    uint32_t hcount = 0;                      // chunks processed by this CTA (selects the h tile buffer)
     const uint32_t ltempty[2] = {map_to_cta(tempty_bar(0), 0), map_to_cta(tempty_bar(1), 0)};
     pair_walk(p, [&](int cp, int l, int t, int s, int d, int mp) {
       if (cp != bias_cp || l != bias_layer) {
@@ -234,34 +242,51 @@ lstm_seq2_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(ltempty[acc]);       // the leader's MMA issuer waits for both CTAs
         });
-        if (et == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        named_bar_sync(2, ET);
+        // h_t of this chunk: each warp drops its [32 x 16] piece into the swizzled [128 x 64] tile of buffer hb and moves on;
+        // the store warp ships the tile with one TMA store once all 16 pieces are there (no CTA-wide barrier on this path)
         {
+          const int hb = (int)(hcount & 1u);
+          mbar_wait(hfree_bar(hb), ((hcount >> 1) & 1u) ^ 1u);
           const uint32_t rr = (uint32_t)(q * 32 + lane);
-          const uint32_t rowp = htile + rr * 128u;
+          const uint32_t rowp = htile + (uint32_t)hb * P_HTILE_BYTES + rr * 128u;
           sts128(rowp + (((uint32_t)(2 * cs) ^ (rr & 7u)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
           sts128(rowp + (((uint32_t)(2 * cs + 1) ^ (rr & 7u)) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
-        }
-        fence_proxy_async();
-        named_bar_sync(2, ET);
-        if (et == 0) {
-          if (mt_ok && !(ablate & 2)) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(&maps.h[d][l])), "r"(htile), "r"(ch * 64), "r"((t + 1) * cap + mt * 128)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            store_pending = true;
-          }
-          if (ch == P_CHUNKS - 1) {
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            mbar_arrive(hready_bar(s));
-            store_pending = false;
-          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(hfull_bar(hb));
+          ++hcount;
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
     });
+  } else {
+    // ================= h_t store warp (both CTAs) =================
+    if (lane == 0) {
+      uint32_t hcount = 0;
+      pair_walk(p, [&](int, int l, int t, int s, int d, int mp) {
+        const int mt = 2 * mp + (int)rank;
+        const bool mt_ok = mt < m_tiles;
+        for (int ch = 0; ch < P_CHUNKS; ++ch) {
+          const int hb = (int)(hcount & 1u);
+          mbar_wait(hfull_bar(hb), (hcount >> 1) & 1u);
+          if (mt_ok && !(ablate & 2)) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&maps.h[d][l])), "r"(htile + (uint32_t)hb * P_HTILE_BYTES), "r"(ch * 64), "r"((t + 1) * cap + mt * 128)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the tile has been read: the epilogue may rewrite it
+          mbar_arrive(hfree_bar(hb));
+          if (ch == P_CHUNKS - 1) {
+            // publish h_t: stores complete (async proxy) -> this CTA's TMA producer may load them for the next step
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            mbar_arrive(hready_bar(s));
+          }
+          ++hcount;
+        }
+      });
+    }
   }
 
   tc_fence_before();

@@ -220,6 +220,13 @@ def test_persistent_lstm_kernel_matches_per_step_launches(engine, ckpt, precisio
     print("\n[lstm seq vs per-step, {}, n={}] max|dp|={:.3e} identical={}".format(precision, n, d, np.array_equal(a, b)))
     assert np.array_equal(a, b)
     assert np.array_equal(pa, pb)
+    # the default is the CTA-pair kernel (lstm_seq2.cu); the single-CTA one (lstm_seq.cu) must agree bit for bit as well
+    monkeypatch.setenv("DSB_LSTM_PAIR", "0")
+    engine.load_weights(ckpt)
+    c, pc = engine.forward(*x, precision=precision)
+    monkeypatch.delenv("DSB_LSTM_PAIR")
+    assert np.array_equal(a, c)
+    assert np.array_equal(pa, pc)
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])
