@@ -229,52 +229,64 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   const float* wr = hw + ncnn;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  for (int64_t s = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); s < p.n; s += (int64_t)gridDim.x * wpb) {
-    float a0 = 0.f, a1 = 0.f;
+  // A warp takes HS consecutive samples per iteration so that every weight vector read from shared memory is used HS times
+  // (the kernel was bound by the shared-memory pipe: 44 KB of weight reads per 11 KB of activations).  The per-sample FMA
+  // order is unchanged.
+  constexpr int HS = 4;
+  for (int64_t s0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * HS; s0 < p.n; s0 += (int64_t)gridDim.x * wpb * HS) {
+    float a0[HS], a1[HS];
+#pragma unroll
+    for (int k = 0; k < HS; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
+    const int ns = (int)((p.n - s0) < HS ? (p.n - s0) : HS);
     if (p.y != nullptr) {
-      const T* y = reinterpret_cast<const T*>(p.y) + s * p.Lp * p.ldy;
-      const int nv = p.L * CH / 8;                 // rows 0..L-1 of this sample, 30 vectors of 8 channels per row
+      const T* y = reinterpret_cast<const T*>(p.y) + s0 * p.Lp * p.ldy;
+      const size_t sstride = (size_t)p.Lp * p.ldy;
+      const int nv = p.L * CH / 8;                 // rows 0..L-1 of a sample, 30 vectors of 8 channels per row
       for (int i = lane; i < nv; i += 32) {
-        const Vec8<T> v = Vec8<T>::load(y + (i / (CH / 8)) * p.ldy + (i % (CH / 8)) * 8);
+        const size_t off = (size_t)(i / (CH / 8)) * p.ldy + (i % (CH / 8)) * 8;
+        Vec8<T> v[HS];
+#pragma unroll
+        for (int k = 0; k < HS; ++k) v[k] = Vec8<T>::load(y + (k < ns ? k : 0) * sstride + off);
         const float4* w = reinterpret_cast<const float4*>(hw + (size_t)i * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 ww = w[q];
-          a0 = fmaf(v.v[2 * q], ww.x, a0); a1 = fmaf(v.v[2 * q], ww.y, a1);
-          a0 = fmaf(v.v[2 * q + 1], ww.z, a0); a1 = fmaf(v.v[2 * q + 1], ww.w, a1);
+#pragma unroll
+          for (int k = 0; k < HS; ++k) {
+            a0[k] = fmaf(v[k].v[2 * q], ww.x, a0[k]); a1[k] = fmaf(v[k].v[2 * q], ww.y, a1[k]);
+            a0[k] = fmaf(v[k].v[2 * q + 1], ww.z, a0[k]); a1[k] = fmaf(v[k].v[2 * q + 1], ww.w, a1[k]);
+          }
         }
       }
     }
     if (p.hfw != nullptr) {
-      const T* hf = reinterpret_cast<const T*>(p.hfw) + s * HID;
-      const T* hb = reinterpret_cast<const T*>(p.hbw) + s * HID;
-      {
-        const Vec8<T> v = Vec8<T>::load(hf + lane * 8);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const T* hsrc = reinterpret_cast<const T*>(half == 0 ? p.hfw : p.hbw) + s0 * HID;
+        Vec8<T> v[HS];
+#pragma unroll
+        for (int k = 0; k < HS; ++k) v[k] = Vec8<T>::load(hsrc + (size_t)(k < ns ? k : 0) * HID + lane * 8);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float2 ww = reinterpret_cast<const float2*>(wr)[lane * 8 + q];
-          a0 = fmaf(v.v[q], ww.x, a0); a1 = fmaf(v.v[q], ww.y, a1);
-        }
-      }
-      {
-        const Vec8<T> v = Vec8<T>::load(hb + lane * 8);
+          const float2 ww = reinterpret_cast<const float2*>(wr)[half * HID + lane * 8 + q];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float2 ww = reinterpret_cast<const float2*>(wr)[HID + lane * 8 + q];
-          a0 = fmaf(v.v[q], ww.x, a0); a1 = fmaf(v.v[q], ww.y, a1);
+          for (int k = 0; k < HS; ++k) { a0[k] = fmaf(v[k].v[q], ww.x, a0[k]); a1[k] = fmaf(v[k].v[q], ww.y, a1[k]); }
         }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    }
-    if (lane == 0) {
-      const float p0 = 1.0f / (1.0f + expf(-a0)), p1 = 1.0f / (1.0f + expf(-a1));
-      p.probs[2 * s] = p0;
-      p.probs[2 * s + 1] = p1;
-      p.pred[s] = (p1 > p0) ? 1 : 0;     // argmax, ties -> 0
+    for (int k = 0; k < HS; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a0[k] += __shfl_xor_sync(0xffffffffu, a0[k], o);
+        a1[k] += __shfl_xor_sync(0xffffffffu, a1[k], o);
+      }
+      if (lane == 0 && k < ns) {
+        const float p0 = 1.0f / (1.0f + expf(-a0[k])), p1 = 1.0f / (1.0f + expf(-a1[k]));
+        p.probs[2 * (s0 + k)] = p0;
+        p.probs[2 * (s0 + k) + 1] = p1;
+        p.pred[s0 + k] = (p1 > p0) ? 1 : 0;     // argmax, ties -> 0
+      }
     }
   }
 }

@@ -786,7 +786,7 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
           DSB_CUDA(cudaFuncSetAttribute(head_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
           head_cfg[ctx->device & 63] = true;
         }
-        const unsigned hgrid = (unsigned)std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 3);
+        const unsigned hgrid = (unsigned)std::min<int64_t>((n + 31) / 32, (int64_t)ctx->sm_count * 3);      // 8 warps x 4 samples per block iteration
         head_kernel<T><<<hgrid, 256, hsm, s>>>(p);
         DSB_CUDA(cudaGetLastError());
         ctx->launches++;
