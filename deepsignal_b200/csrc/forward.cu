@@ -38,6 +38,7 @@ struct Step {
   LstmSeqLaunch seq;
   FrontLaunch front;
   bool lstm_pair = true;      // DSB_LSTM_PAIR=0: single-CTA sequence kernel (lstm_seq.cu) instead of the CTA-pair one (lstm_seq2.cu)
+  bool a_pair = false;        // DSB_A_PAIR=1: CTA-pair variant of inception kernel A (incept_a2.cu)
   bool front_cc = false;      // DSB_FRONT=1: CUDA-core stem (front_tc.cu, bit-identical to the separate launches) instead of front2_tc.cu
   int epi_kind = EPI_CONV;
   int kclass = KC_GEMM;
@@ -370,6 +371,7 @@ struct Builder {
             float* biasA = reinterpret_cast<float*>(wa.take(240 * sizeof(float)));
             float* biasB = reinterpret_cast<float*>(wa.take(208 * sizeof(float)));
             Step sa, sb;
+            { const char* ev = getenv("DSB_A_PAIR"); sa.a_pair = ev && ev[0] == '1'; }
             sa.kind = ST_INCEPT_A; sa.stream = 0; sa.rows_per_sample = Lp; sa.kclass = KC_INCEPT_A;
             sb.kind = ST_INCEPT_B; sb.stream = 0; sb.rows_per_sample = Lp; sb.kclass = KC_GEMM;
             sa.flops_per_row = 2.0 * (double)cin * 240.0 * (double)L / (double)Lp;
@@ -393,6 +395,9 @@ struct Builder {
               encode_map_16(&A.maps.p4s, TP4, rows_cap, 32, 32, 32, 32, f16);
               encode_map_16(&A.maps.p5s, TP5, rows_cap, 32, 32, 32, 32, f16);
               encode_map_16(&A.maps.pss, TPS, rows_cap, 48, 48, 32, 32, f16);
+              A.maps2 = A.maps;
+              encode_map_16(&A.maps2.wp1, Wp1.w, 192, Wp1.Ktot, Wp1.Ktot, 96, 64, f16);
+              encode_map_16(&A.maps2.wb1, Wb1.w, 48, Wb1.Ktot, Wb1.Ktot, 24, 64, f16);
               for (int k = 0; k < 240; ++k) A.p.biasv[k] = ha[k];
               A.p.Lp = Lp; A.p.L = L; A.p.Y = Y; A.p.ldY = YLD; A.p.P3 = TP3; A.p.P4 = TP4; A.p.P5 = TP5; A.p.PS = TPS; A.p.bias = biasA;
               InceptBLaunch& B = sb.ib;
@@ -681,7 +686,8 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_INCEPT_A: {
         if constexpr (!std::is_same<T, float>::value) {
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
-          launch_incept_a(st.ia, (int)M, sms[st.stream], s);
+          if (st.a_pair) launch_incept_a2(st.ia, (int)M, sms[st.stream], s);
+          else launch_incept_a(st.ia, (int)M, sms[st.stream], s);
           ctx->launches++;
         }
         break;

@@ -24,7 +24,7 @@ struct InceptAParams {
   const float* bias = nullptr; // [240]: b1 (48) then p1 (b2 48 | b3a 32 | b4a 32 | b5a 32 | stem 48)
   float biasv[240];            // the same values by value: read through the constant bank (LDC), not shared memory
 };
-struct InceptALaunch { InceptAMaps maps; InceptAParams p; bool fp16 = false; };
+struct InceptALaunch { InceptAMaps maps; InceptAMaps maps2; InceptAParams p; bool fp16 = false; };   // maps2: weight maps with half-height boxes (CTA-pair kernel)
 
 struct alignas(64) InceptBMaps { CUtensorMap t3, t4, t5, w3, w4, w5b, w5c, ys; };   // ys: Y as [32 x 32] store boxes
 struct InceptBParams {
@@ -41,5 +41,6 @@ constexpr int INCEPT_A_TILE_ROWS = 126;   // 128-row tiles overlap by one row on
 
 void launch_incept_a(const InceptALaunch& L, int M, int sm_count, cudaStream_t s);
 void launch_incept_b(const InceptBLaunch& L, int M, int sm_count, cudaStream_t s);
+void launch_incept_a2(const InceptALaunch& L, int M, int sm_count, cudaStream_t s);   // CTA-pair variant of kernel A (incept_a2.cu)
 
 }  // namespace dsb
