@@ -128,7 +128,7 @@ def test_chunking_and_ragged_sizes_are_batch_invariant(engine, ckpt, precision):
     engine.set_max_chunk(256)
     chunked, pch = engine.forward(*x, precision=precision)
     assert np.array_equal(full, chunked) and np.array_equal(pfull, pch)
-    for n in (1, 7, 127, 129):
+    for n in (1, 7, 127, 129, 300, 385, 641):       # 1, 2, 3 (odd: a partner-less CTA in the pair kernels), 4 and 6 tiles of 128
         part, _ = engine.forward(*[a[:n] for a in x], precision=precision)
         assert np.array_equal(part, full[:n]), n
     engine.set_max_chunk(8192)
