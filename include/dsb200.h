@@ -88,7 +88,9 @@ DSB_API const char* dsb_last_error(const dsb_ctx* ctx);   /* ctx may be NULL: la
 DSB_API int dsb_load_weights(dsb_ctx* ctx, const dsb_tensor* tensors, int32_t n_tensors,
                      uint32_t flags, int32_t kmer_len, int32_t signal_len);
 
-/* Largest number of samples processed per internal pass (workspace grows with it). */
+/* Largest number of samples processed per internal pass (workspace grows with it: ~330 KB per sample on the 16-bit
+ * paths).  Default 37888 = 148 SMs x 256 samples, the size at which the persistent LSTM kernel is perfectly balanced;
+ * smaller values (multiples of 128) trade throughput for memory. */
 DSB_API int dsb_set_max_chunk(dsb_ctx* ctx, int64_t max_chunk);
 DSB_API size_t dsb_workspace_bytes(const dsb_ctx* ctx, int64_t n, int32_t precision);
 
