@@ -25,16 +25,27 @@ __device__ __forceinline__ void st_c(float4* p, float4 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
 }
 
-template <bool F16, class Release>
+// Loads this lane's four cell-state float4 of a group (call it BEFORE waiting for the accumulator: the L2 latency then
+// overlaps the MMA wait instead of sitting in the epilogue's critical path).
+__device__ __forceinline__ void lstm_load_c(const float4* cblk, bool c_in, float4 (&c4)[4]) {
+  const uint64_t pol = l2_policy_evict_last();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c4[i] = c_in ? ld_c(cblk + i * 32, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <bool F16, bool PRELOADED = false, class Release>
 __device__ __forceinline__ void lstm_epi_group(uint32_t t_addr, float4* cblk, bool c_in, bool c_out, const float* bias,
-                                               uint32_t (&pk)[8], int ablate, Release&& release) {
+                                               uint32_t (&pk)[8], int ablate, Release&& release, const float4* c4 = nullptr) {
   using namespace tc;
   const uint64_t pol = l2_policy_evict_last();
 #pragma unroll
   for (int sub = 0; sub < 2; ++sub) {
     // the cell state is private to this CTA and was written one step (~20 us) ago: L2 hits
     float4 cprev[2];
-    if (c_in) {
+    if constexpr (PRELOADED) {
+      cprev[0] = c4[2 * sub];
+      cprev[1] = c4[2 * sub + 1];
+    } else if (c_in) {
       cprev[0] = ld_c(cblk + (2 * sub) * 32, pol);
       cprev[1] = ld_c(cblk + (2 * sub + 1) * 32, pol);
     } else {

@@ -231,17 +231,19 @@ lstm_seq2_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p
       const bool mt_ok = mt < m_tiles;
       const bool c_in = t > 0 && mt_ok && !(ablate & 1), c_out = t + 1 < p.KL && mt_ok && !(ablate & 1);
       for (int ch = 0; ch < P_CHUNKS; ++ch) {
+        const int col = ch * 256 + cs * 64;
+        float4* cblk = reinterpret_cast<float4*>(p.c[d]) + ((((size_t)(mt_ok ? mt : 0) * (GATES / 64) + (size_t)(col >> 6)) * 4 + q) * 4) * 32 + lane;
+        float4 c4[4];
+        lstm_load_c(cblk, c_in, c4);                               // in flight while this warp waits for the accumulator
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-        const int col = ch * 256 + cs * 64;
-        float4* cblk = reinterpret_cast<float4*>(p.c[d]) + ((((size_t)(mt_ok ? mt : 0) * (GATES / 64) + (size_t)(col >> 6)) * 4 + q) * 4) * 32 + lane;
         uint32_t pk[8];
-        lstm_epi_group<F16>(t_row + (uint32_t)(cs * 64), cblk, c_in, c_out, sb + col, pk, ablate, [&]() {
+        lstm_epi_group<F16, true>(t_row + (uint32_t)(cs * 64), cblk, c_in, c_out, sb + col, pk, ablate, [&]() {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(ltempty[acc]);       // the leader's MMA issuer waits for both CTAs
-        });
+        }, c4);
         // h_t of this chunk: each warp drops its [32 x 16] piece into the swizzled [128 x 64] tile of buffer hb and moves on;
         // the store warp ships the tile with one TMA store once all 16 pieces are there (no CTA-wide barrier on this path)
         {
