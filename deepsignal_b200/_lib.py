@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdsb200.so")
+LIB_PATH = os.environ.get("DSB_LIB") or os.path.join(_HERE, "libdsb200.so")   # DSB_LIB: another build of the same ABI (A/B timing)
 
 DSB_OK = 0
 DSB_ERR_CAPACITY = -5
