@@ -1,5 +1,5 @@
 """Debug aid: run the same forward through the in-tree libdsb200.so and a previous build (profiles/experiments/_old/
-libdsb200_prev.so, not tracked) in two processes and compare the probabilities bit for bit."""
+libdsb200_prev.so or $DSB_PREV_LIB, not tracked) in two processes and compare the probabilities bit for bit."""
 import os, subprocess, sys
 import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -20,6 +20,6 @@ p, _ = eng.forward(*x, precision=sys.argv[4]); np.save(sys.argv[2], p)
 for prec in ("bf16", "fp16"):
     for n in (99, 1500):
         subprocess.check_call([sys.executable, "-c", CODE, "cur", "/tmp/cur.npy", str(n), prec])
-        subprocess.check_call([sys.executable, "-c", CODE, os.path.join(HERE, "_old", "libdsb200_prev.so"), "/tmp/prev.npy", str(n), prec])
+        subprocess.check_call([sys.executable, "-c", CODE, os.environ.get("DSB_PREV_LIB", os.path.join(HERE, "_old", "libdsb200_prev.so")), "/tmp/prev.npy", str(n), prec])
         a, b = np.load("/tmp/cur.npy"), np.load("/tmp/prev.npy")
         print(prec, n, "identical to previous build:", np.array_equal(a, b), float(np.abs(a - b).max()))
