@@ -10,6 +10,7 @@
 #include <array>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <type_traits>
 
 #include "elementwise.cuh"
@@ -20,7 +21,7 @@
 
 namespace dsb {
 
-enum StepKind { ST_GEMM, ST_STEM, ST_POOL1, ST_POOL2, ST_FEAT, ST_HEAD, ST_ZERO, ST_INCEPT_A, ST_INCEPT_B, ST_LSTM_SEQ, ST_FRONT, ST_DEBUG_CMP };
+enum StepKind { ST_GEMM, ST_STEM, ST_POOL1, ST_POOL2, ST_FEAT, ST_HEAD, ST_ZERO, ST_INCEPT_A, ST_INCEPT_B, ST_LSTM_SEQ, ST_FRONT, ST_DEBUG_CMP, ST_INCEPT_F };
 
 struct SegHost { const void* a; int ld; int cols; int col0; int drow; int K; int map_rows_per_sample; };
 
@@ -38,6 +39,7 @@ struct Step {
   LstmSeqLaunch seq;
   FrontLaunch front;
   bool lstm_pair = true;      // DSB_LSTM_PAIR=0: single-CTA sequence kernel (lstm_seq.cu) instead of the CTA-pair one (lstm_seq2.cu)
+  std::shared_ptr<void> fused_ab;   // DSB_AB_FUSED=1: the whole block as one kernel (incept_f.cu)
   bool a_pair = false;        // DSB_A_PAIR=1: CTA-pair variant of inception kernel A (incept_a2.cu)
   bool front_cc = false;      // DSB_FRONT=1: CUDA-core stem (front_tc.cu, bit-identical to the separate launches) instead of front2_tc.cu
   int epi_kind = EPI_CONV;
@@ -413,8 +415,17 @@ struct Builder {
               for (int k = 0; k < 208; ++k) B.p.biasv[k] = hb[k];
               B.p.Lp = Lp; B.p.L = L; B.p.PS = TPS; B.p.Y = Y; B.p.ldY = YLD; B.p.bias = biasB;
             }
-            plan.steps.push_back(sa);
-            plan.steps.push_back(sb);
+            const char* fev = getenv("DSB_AB_FUSED");
+            if (fev && fev[0] == '1') {
+              Step sf;
+              sf.kind = ST_INCEPT_F; sf.stream = 0; sf.rows_per_sample = Lp; sf.kclass = KC_INCEPT_A;
+              sf.flops_per_row = sa.flops_per_row + sb.flops_per_row;
+              if (place) sf.fused_ab = std::shared_ptr<void>(make_incept_f(sa.ia, sb.ib, sa.ia.maps2.wp1, sa.ia.maps.wb1), free_incept_f);
+              plan.steps.push_back(sf);
+            } else {
+              plan.steps.push_back(sa);
+              plan.steps.push_back(sb);
+            }
           }
         } else {
         {   // branch-1 max pool (1x3, stride 1)
@@ -688,6 +699,14 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
           if (st.a_pair) launch_incept_a2(st.ia, (int)M, sms[st.stream], s);
           else launch_incept_a(st.ia, (int)M, sms[st.stream], s);
+          ctx->launches++;
+        }
+        break;
+      }
+      case ST_INCEPT_F: {
+        if constexpr (!std::is_same<T, float>::value) {
+          Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
+          launch_incept_f(st.fused_ab.get(), (int)M, sms[st.stream], s);
           ctx->launches++;
         }
         break;

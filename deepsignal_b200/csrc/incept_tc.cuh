@@ -42,5 +42,9 @@ constexpr int INCEPT_A_TILE_ROWS = 126;   // 128-row tiles overlap by one row on
 void launch_incept_a(const InceptALaunch& L, int M, int sm_count, cudaStream_t s);
 void launch_incept_b(const InceptBLaunch& L, int M, int sm_count, cudaStream_t s);
 void launch_incept_a2(const InceptALaunch& L, int M, int sm_count, cudaStream_t s);   // CTA-pair variant of kernel A (incept_a2.cu)
+// single-kernel inception block (incept_f.cu, opt-in): built from the A / B launch descriptions of the same block
+void* make_incept_f(const InceptALaunch& A, const InceptBLaunch& B, const CUtensorMap& wp1_half, const CUtensorMap& wb1_full);
+void free_incept_f(void* h);
+void launch_incept_f(const void* h, int M, int sm_count, cudaStream_t s);
 
 }  // namespace dsb

@@ -270,3 +270,18 @@ def test_repeated_runs_are_bit_identical(engine, ckpt, precision):
     for _ in range(6):
         got, pred = engine.forward(*x, precision=precision)
         assert np.array_equal(got, ref) and np.array_equal(pred, pref)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_single_kernel_inception_block_matches_two_kernel_path(engine, ckpt, precision, monkeypatch):
+    """incept_f.cu (opt-in DSB_AB_FUSED=1: kernels A and B of a block fused, planes never leave the SM, p1 on CTA pairs,
+    thread-fed GEMMs as CTA-local MMAs) must be bit-identical to the default A + B path, including an odd tile count."""
+    x = _inputs(1100, 31)
+    engine.load_weights(ckpt)
+    a, pa = engine.forward(*x, precision=precision)
+    monkeypatch.setenv("DSB_AB_FUSED", "1")
+    engine.load_weights(ckpt)
+    b, pb = engine.forward(*x, precision=precision)
+    monkeypatch.delenv("DSB_AB_FUSED")
+    engine.load_weights(ckpt)
+    assert np.array_equal(a, b) and np.array_equal(pa, pb)
