@@ -71,8 +71,8 @@ def _read_features_file(features_file, features_batch_q, f5_batch_num=20):
 def _call_mods(features_batch, engine, model, init_learning_rate, batch_size):
     """Mirror of reference ``_call_mods`` (:149-194): returns (pred_str, accuracy, batch_num).
 
-    ``engine`` plays the role of the TF session, ``model`` carries the precision ("fp32", "fp16",
-    "bf16").  ``init_learning_rate`` is accepted for signature compatibility and unused (the
+    ``engine`` plays the role of the TF session, ``model`` carries the precision ("fp32", "fp16x2",
+    "fp16", "bf16").  ``init_learning_rate`` is accepted for signature compatibility and unused (the
     reference only feeds it to a placeholder)."""
     sampleinfo, kmers, base_means, base_stds, base_signal_lens, cent_signals, labels = features_batch
     labels = np.reshape(labels, (len(labels)))
@@ -82,7 +82,7 @@ def _call_mods(features_batch, engine, model, init_learning_rate, batch_size):
     kmers_a = np.asarray(kmers, dtype=np.int32)
     probs, prediction = engine.forward(kmers_a, np.asarray(base_means, np.float32), np.asarray(base_stds, np.float32),
                                        np.asarray(base_signal_lens, np.float32), np.asarray(cent_signals, np.float32),
-                                       precision=getattr(model, "precision", "fp16"))
+                                       precision=getattr(model, "precision", "fp16x2"))
     prediction = prediction.astype(np.int64)
     batch_num = 0
     accuracys = []
@@ -114,7 +114,7 @@ def _write_predstr_to_file(write_fp, predstr_q):
 class _ModelHandle(object):
     """What the reference's ``Model(base_num, signal_num, class_num, ...)`` is to ``_call_mods``."""
 
-    def __init__(self, base_num, signal_num, class_num, is_cnn=True, is_base=True, is_rnn=True, precision="fp16"):
+    def __init__(self, base_num, signal_num, class_num, is_cnn=True, is_base=True, is_rnn=True, precision="fp16x2"):
         if not (is_cnn or is_rnn):
             raise ValueError("at least one of is_cnn/is_rnn should be True")
         if class_num != 2:
@@ -156,7 +156,7 @@ def _features_batches_from_reads(reads_path, engine, f5_args, kmer_len, cent_sig
 
 def call_mods(input_path, model_path, result_file, kmer_len, cent_signals_len,
               batch_size, learning_rate, class_num, nproc, is_gpu, is_rnn, is_base, is_cnn,
-              f5_args, precision="fp16", device=0):
+              f5_args, precision="fp16x2", device=0):
     """Same positional signature as the reference ``call_mods`` (:417-495) plus ``precision`` /
     ``device``.  ``is_gpu`` is accepted for compatibility; this implementation always runs on the
     GPU and fails loudly if none is present."""

@@ -7,6 +7,15 @@
 namespace {
 std::string g_create_error;
 
+// read-and-reset of the head kernel's non-finite-logit counter (the caller has synchronised the producing stream)
+int64_t take_nonfinite(dsb_ctx* ctx) {
+  if (!ctx->nonfinite_dev) return 0;
+  int h = 0;
+  DSB_CUDA(cudaMemcpy(&h, ctx->nonfinite_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h != 0) DSB_CUDA(cudaMemset(ctx->nonfinite_dev, 0, sizeof(int)));
+  return h;
+}
+
 template <class F> int guarded(dsb_ctx* ctx, F&& f) {
   try {
     f();
@@ -70,6 +79,7 @@ int dsb_destroy(dsb_ctx* ctx) {
   cudaDeviceSynchronize();
   for (auto& p : ctx->plan) p.reset();
   ctx->xw.reset();
+  if (ctx->nonfinite_dev) cudaFree(ctx->nonfinite_dev);
   for (cudaStream_t s : {ctx->stream_h2d, ctx->stream_compute, ctx->stream_d2h}) if (s) cudaStreamDestroy(s);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
@@ -98,6 +108,30 @@ int dsb_set_max_chunk(dsb_ctx* ctx, int64_t max_chunk) {
   return guarded(ctx, [&] {
     if (max_chunk < 128 || max_chunk > (1 << 20)) dsb::fail(DSB_ERR_INVALID, "max_chunk must be in [128, 1048576]");
     ctx->max_chunk = (max_chunk + 127) / 128 * 128;
+  });
+}
+
+int dsb_get_plan_options(const dsb_ctx* ctx, dsb_plan_options* out) {
+  if (!ctx || !out) return DSB_ERR_INVALID;
+  *out = ctx->opts;
+  return DSB_OK;
+}
+
+int dsb_set_plan_options(dsb_ctx* ctx, const dsb_plan_options* opts) {
+  if (!ctx || !opts) return DSB_ERR_INVALID;
+  return guarded(ctx, [&] {
+    DSB_CUDA(cudaSetDevice(ctx->device));
+    DSB_CUDA(cudaDeviceSynchronize());          // no launch of an old plan may still be in flight
+    for (auto& p : ctx->plan) p.reset();
+    ctx->opts = *opts;
+  });
+}
+
+int dsb_nonfinite_count(dsb_ctx* ctx, int64_t* count) {
+  if (!ctx || !count) return DSB_ERR_INVALID;
+  return guarded(ctx, [&] {
+    DSB_CUDA(cudaSetDevice(ctx->device));
+    *count = take_nonfinite(ctx);
   });
 }
 
@@ -173,6 +207,10 @@ int dsb_forward_host(dsb_ctx* ctx, int32_t precision, int64_t n, const int32_t* 
     DSB_CUDA(cudaStreamSynchronize(ctx->stream_d2h));
     DSB_CUDA(cudaStreamSynchronize(ctx->stream_compute));
     if (ctx->prof.enabled) ctx->prof.collect();
+    const int64_t bad = take_nonfinite(ctx);
+    if (bad > 0)
+      dsb::fail(DSB_ERR_NONFINITE, "%lld of %lld samples have non-finite logits (16-bit activation overflow; outputs were written, "
+                "rerun with DSB_PREC_FP32)", (long long)bad, (long long)n);
   });
 }
 

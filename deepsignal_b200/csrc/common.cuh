@@ -175,7 +175,9 @@ struct dsb_ctx {
   bool have_model = false;
   dsb::FoldedModel model;
   dsb::Profiler prof;
-  std::unique_ptr<dsb::ForwardPlan, dsb::PlanDeleter> plan[3];   // per precision
+  std::unique_ptr<dsb::ForwardPlan, dsb::PlanDeleter> plan[4];   // per precision
+  dsb_plan_options opts{1, 1, 1, 0, 0, 0, 0};
+  int* nonfinite_dev = nullptr;   // device counter written by the head kernel
   std::unique_ptr<dsb::ExtractWork, dsb::ExtractDeleter> xw;
   // staging for the _host entry points
   dsb::DevBuf stage_in[2], stage_out[2];

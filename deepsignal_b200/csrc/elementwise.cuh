@@ -81,6 +81,7 @@ struct StemParams {
   int L1, L2, Lp2, conv_pl, pool_pl;
   void* out;           // [n*Lp2][64]
   int n;
+  long long lo_off = 0;  // split-operand mode: element offset of the lo twin of `out` (0 = single 16-bit output)
 };
 
 template <class T>
@@ -135,7 +136,9 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
     slide();
     const float c2 = conv_here();
     const float best = (pos < p.L2) ? fmaxf(c0, fmaxf(c1, c2)) : 0.f;
-    out[(size_t)pos * 64 + c] = from_f32<T>(best);
+    const T hi = from_f32<T>(best);
+    out[(size_t)pos * 64 + c] = hi;
+    if (p.lo_off != 0) out[(size_t)pos * 64 + c + p.lo_off] = from_f32<T>(best - to_f32<T>(hi));
     c0 = c2;
   }
 }
@@ -160,6 +163,70 @@ __global__ void pool3s1_kernel(const T* __restrict__ x, T* __restrict__ y, int64
     for (int i = 0; i < 8; ++i) a.v[i] = fmaxf(a.v[i], b.v[i]);
   }
   a.store(y + r * ld + c);
+}
+
+// ---- split-operand variants: a value is the pair (hi, lo) with v = hi + lo, |lo| <= ulp(hi)/2.  hi is a monotone
+// rounding of v, so ordering pairs by hi and then by lo orders them by v exactly; the pooled pair is one of the inputs.
+struct Pair8 {
+  float h[8], l[8];
+  __device__ __forceinline__ static Pair8 load(const __half* p, long long lo_off) {
+    Pair8 r;
+    const Vec8<__half> a = Vec8<__half>::load(p), b = Vec8<__half>::load(p + lo_off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r.h[i] = a.v[i]; r.l[i] = b.v[i]; }
+    return r;
+  }
+  __device__ __forceinline__ void take_max(const Pair8& o) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool gt = o.h[i] > h[i] || (o.h[i] == h[i] && o.l[i] > l[i]);
+      h[i] = gt ? o.h[i] : h[i];
+      l[i] = gt ? o.l[i] : l[i];
+    }
+  }
+  __device__ __forceinline__ void store(__half* p, long long lo_off) const {
+    Vec8<__half> a, b;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a.v[i] = h[i]; b.v[i] = l[i]; }
+    a.store(p);
+    b.store(p + lo_off);
+  }
+};
+
+__global__ void pool3s1_split_kernel(const __half* __restrict__ x, __half* __restrict__ y, int64_t M, int C, int ld,
+                                     long long lo_in, long long lo_out) {
+  const int cv = C / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * cv) return;
+  const int64_t r = idx / cv;
+  const int c = (int)(idx % cv) * 8;
+  Pair8 a = Pair8::load(x + r * ld + c, lo_in);
+  if (r > 0) a.take_max(Pair8::load(x + (r - 1) * ld + c, lo_in));
+  if (r + 1 < M) a.take_max(Pair8::load(x + (r + 1) * ld + c, lo_in));
+  a.store(y + r * ld + c, lo_out);
+}
+
+__global__ void pool3s2_split_kernel(const __half* __restrict__ x, __half* __restrict__ y, int64_t n, int C, int ld,
+                                     int Lin, int Lpin, int Lout, int Lpout, int pl, long long lo_in, long long lo_out) {
+  const int cv = C / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * Lpout * cv) return;
+  const int c = (int)(idx % cv) * 8;
+  const int64_t ro = idx / cv;
+  const int64_t s = ro / Lpout;
+  const int po = (int)(ro % Lpout);
+  Pair8 a;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a.h[i] = 0.f; a.l[i] = 0.f; }       // activations are >= 0 (post-ReLU)
+  if (po < Lout) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int q = 2 * po - pl + k;
+      if (q < 0 || q >= Lin) continue;
+      a.take_max(Pair8::load(x + (s * Lpin + q) * ld + c, lo_in));
+    }
+  }
+  a.store(y + ro * ld + c, lo_out);
 }
 
 // ---- maxpool 1x3 stride 2 SAME between stages (reference layers.py:211-213,224-226) ----------------
@@ -217,6 +284,8 @@ struct HeadParams {
   const float* Wc;                    // [L*240][2]
   const float* Wr;                    // [512][2]
   float* probs; int32_t* pred; int64_t n;
+  long long y_lo_off = 0;             // split-operand mode: element offset of the lo twin of y (0 = single 16-bit values)
+  int* nonfinite = nullptr;           // device counter: samples whose logits are not finite (overflowed 16-bit activations)
 };
 
 template <class T>
@@ -247,6 +316,14 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
         Vec8<T> v[HS];
 #pragma unroll
         for (int k = 0; k < HS; ++k) v[k] = Vec8<T>::load(y + (k < ns ? k : 0) * sstride + off);
+        if (p.y_lo_off != 0) {
+#pragma unroll
+          for (int k = 0; k < HS; ++k) {
+            const Vec8<T> lo = Vec8<T>::load(y + (k < ns ? k : 0) * sstride + off + p.y_lo_off);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[k].v[e] += lo.v[e];
+          }
+        }
         const float4* w = reinterpret_cast<const float4*>(hw + (size_t)i * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -282,6 +359,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
         a1[k] += __shfl_xor_sync(0xffffffffu, a1[k], o);
       }
       if (lane == 0 && k < ns) {
+        if (p.nonfinite != nullptr && !(isfinite(a0[k]) && isfinite(a1[k]))) atomicAdd(p.nonfinite, 1);
         const float p0 = 1.0f / (1.0f + expf(-a0[k])), p1 = 1.0f / (1.0f + expf(-a1[k]));
         p.probs[2 * (s0 + k)] = p0;
         p.probs[2 * (s0 + k) + 1] = p1;

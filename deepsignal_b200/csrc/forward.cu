@@ -1,7 +1,8 @@
 // forward.cu — the call_mods forward (reference model.py:57-108 + layers.py) as a static plan of
 // GEMM-with-epilogue ops and a few HBM-bound helpers, executed chunk by chunk on device-resident
-// inputs.  Two backends share the plan: fp32 CUDA-core GEMMs (DSB_PREC_FP32) and bf16 tcgen05
-// GEMMs (DSB_PREC_BF16).
+// inputs.  Two backends share the plan: fp32 CUDA-core GEMMs (DSB_PREC_FP32) and 16-bit tcgen05 GEMMs
+// (DSB_PREC_BF16 / DSB_PREC_FP16, and DSB_PREC_FP16X2 = the same kernels on split hi + lo fp16 activations).
+// Which kernels realise the plan (fused or one launch per conv) comes from ctx->opts (dsb_plan_options).
 //
 // Activation layout ("padded rows"): a stage with L positions stores sample s, position p at row
 // s*(L+HALO)+p of a row-major [rows][C] matrix; the HALO rows after each sample are zero, so a k-tap
@@ -21,9 +22,9 @@
 
 namespace dsb {
 
-enum StepKind { ST_GEMM, ST_STEM, ST_POOL1, ST_POOL2, ST_FEAT, ST_HEAD, ST_ZERO, ST_INCEPT_A, ST_INCEPT_B, ST_LSTM_SEQ, ST_FRONT, ST_DEBUG_CMP, ST_INCEPT_F };
+enum StepKind { ST_GEMM, ST_STEM, ST_POOL1, ST_POOL2, ST_FEAT, ST_HEAD, ST_ZERO, ST_INCEPT_A, ST_INCEPT_B, ST_LSTM_SEQ, ST_FRONT };
 
-struct SegHost { const void* a; int ld; int cols; int col0; int drow; int K; int map_rows_per_sample; };
+struct SegHost { const void* a; int ld; int cols; int col0; int drow; int K; int map_rows_per_sample; long long lo = 0; };   // lo: element offset of the lo twin (split mode)
 
 struct Step {
   int kind = ST_GEMM;
@@ -32,16 +33,10 @@ struct Step {
   // GEMM
   GemmF32Params f32;
   TcLaunch tc;
-  CUtensorMap b_half;         // LSTM weights with a 128-row box (CTA-pair kernel)
-  bool pair = false;
   InceptALaunch ia;
   InceptBLaunch ib;
   LstmSeqLaunch seq;
   FrontLaunch front;
-  bool lstm_pair = true;      // DSB_LSTM_PAIR=0: single-CTA sequence kernel (lstm_seq.cu) instead of the CTA-pair one (lstm_seq2.cu)
-  std::shared_ptr<void> fused_ab;   // DSB_AB_FUSED=1: the whole block as one kernel (incept_f.cu)
-  bool a_pair = false;        // DSB_A_PAIR=1: CTA-pair variant of inception kernel A (incept_a2.cu)
-  bool front_cc = false;      // DSB_FRONT=1: CUDA-core stem (front_tc.cu, bit-identical to the separate launches) instead of front2_tc.cu
   int epi_kind = EPI_CONV;
   int kclass = KC_GEMM;
   double flops_per_row = 0;
@@ -49,6 +44,7 @@ struct Step {
   StemParams stem;
   const void* src = nullptr; void* dst = nullptr;
   int C = 0, ld = 0, Lin = 0, Lpin = 0, Lout = 0, Lpout = 0, pl = 0;
+  long long lo_in = 0, lo_out = 0;      // split mode: element offsets of the lo twins of src / dst
   size_t zero_bytes_per_sample = 0;
   HeadParams head;
 };
@@ -63,7 +59,6 @@ struct ForwardPlan {
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   bool multi_stream = true;
   size_t work_bytes = 0;
-  std::vector<std::pair<const char*, std::pair<const void*, size_t>>> dbg;   // DSB_DEBUG_SUM: named buffers to checksum after each step
   ~ForwardPlan() {
     for (auto s : side) if (s) cudaStreamDestroy(s);
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -74,25 +69,6 @@ struct ForwardPlan {
 void destroy_plan(ForwardPlan* p) { delete p; }
 
 namespace {
-
-// debug aid (DSB_FRONT_CHECK=1): compare two 16-bit [rows][ld] buffers on cols [0, C), report mismatches
-__global__ void debug_compare_kernel(const uint16_t* a, const uint16_t* b, long long rows, int C, int ld, int Lp, int* count) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * C) return;
-  const long long r = idx / C;
-  const int c = (int)(idx % C);
-  const uint16_t x = a[r * ld + c], y = b[r * ld + c];
-  if (x != y) {
-    const int k = atomicAdd(count, 1);
-    if (k < 24) printf("front mismatch row %lld (sample %lld pos %lld) col %d: fused %04x separate %04x\n", r, r / Lp, r % Lp, c, x, y);
-  }
-}
-
-__global__ void debug_sum_kernel(const uint16_t* a, long long n, unsigned long long* out) {
-  unsigned long long acc = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += a[i] * (unsigned long long)(1 + (i & 1023));
-  atomicAdd(out, acc);
-}
 
 struct Arena {          // bump allocator over one DevBuf (two passes: size, then place)
   uint8_t* base = nullptr;
@@ -140,9 +116,10 @@ DevGemm<T> upload_gemm(Arena& wa, const FoldedGemm& g, const std::vector<std::ar
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-template <class T>
+template <class T, bool SPLIT = false>
 struct Builder {
   static constexpr bool TC = !std::is_same<T, float>::value;
+  static_assert(!SPLIT || std::is_same<T, __half>::value, "the split-operand mode carries fp16 hi + lo parts");
   dsb_ctx* ctx;
   ForwardPlan& plan;
   const FoldedModel& fm;
@@ -152,6 +129,9 @@ struct Builder {
   cudaStream_t up_stream;
 
   T* buf(size_t elems) { return reinterpret_cast<T*>(ba.take(elems * sizeof(T))); }
+  // CNN activation matrix; in split mode its lo twin follows it (`elems` elements further on)
+  T* abuf(size_t elems) { return reinterpret_cast<T*>(ba.take(elems * sizeof(T) * (SPLIT ? 2 : 1))); }
+  static long long lo_of(size_t elems) { return SPLIT ? (long long)elems : 0; }
 
   // one GEMM step -------------------------------------------------------------------------------
   // alg_rows: rows per sample that carry real outputs (L for convs, 1 for the LSTM); kalg: algorithmic K
@@ -184,34 +164,32 @@ struct Builder {
       L.BK = BK;
       L.epi_kind = epi_kind;
       L.fp16 = std::is_same<T, __half>::value;
-      L.p.nseg = (int)segs.size();
       const void* map_base[2] = {nullptr, nullptr};
-      int nmaps = 0, kt = 0;
-      for (int i = 0; i < L.p.nseg; ++i) {
-        int mi = -1;
-        for (int j = 0; j < nmaps; ++j) if (map_base[j] == segs[i].a) mi = j;
-        if (mi < 0) {
-          if (nmaps == 2) fail(DSB_ERR_STATE, "internal: more than two A matrices in one GEMM");
-          mi = nmaps++;
-          map_base[mi] = segs[i].a;
-          encode_map_16(&L.maps.a[mi], segs[i].a, rows_cap, segs[i].cols, segs[i].ld, 128, BK, std::is_same<T, __half>::value);
-        }
+      int nmaps = 0, kt = 0, ns = 0;
+      auto map_of = [&](const void* base, const SegHost& sg) {
+        for (int j = 0; j < nmaps; ++j) if (map_base[j] == base) return j;
+        if (nmaps == 2) fail(DSB_ERR_STATE, "internal: more than two A matrices in one GEMM");
+        map_base[nmaps] = base;
+        encode_map_16(&L.maps.a[nmaps], base, rows_cap, sg.cols, sg.ld, 128, BK, std::is_same<T, __half>::value);
+        return nmaps++;
+      };
+      for (size_t i = 0; i < segs.size(); ++i) {
         const int nkb = round_up(segs[i].K, BK) / BK;
-        L.p.seg[i] = SegTC{mi, segs[i].col0, segs[i].drow, nkb};
+        const int wkb = kt / BK;
+        if (ns + (segs[i].lo ? 2 : 1) > MAX_SEG) fail(DSB_ERR_STATE, "internal: too many GEMM segments");
+        L.p.seg[ns++] = SegTC{map_of(segs[i].a, segs[i]), segs[i].col0, segs[i].drow, nkb, wkb};
+        if (segs[i].lo)      // the lo part multiplies the same weight blocks
+          L.p.seg[ns++] = SegTC{map_of(reinterpret_cast<const T*>(segs[i].a) + segs[i].lo, segs[i]), segs[i].col0, segs[i].drow, nkb, wkb};
         kt += nkb * BK;
       }
+      L.p.nseg = ns;
       if (nmaps == 1) L.maps.a[1] = L.maps.a[0];
-      if (kt != W.Ktot) fail(DSB_ERR_STATE, "internal: bf16 GEMM K mismatch %d vs %d", kt, W.Ktot);
+      if (kt != W.Ktot) fail(DSB_ERR_STATE, "internal: 16-bit GEMM K mismatch %d vs %d", kt, W.Ktot);
       L.p.BN = W.N <= 256 ? W.N : 256;
       L.p.epi = epi;
       L.flops_per_row = st.flops_per_row;
       finalize_tc_launch(L);      // may shrink BN so that the weights stay resident in shared memory
       encode_map_16(&L.maps.b, W.w, W.N, W.Ktot, W.Ktot, L.p.BN, BK, std::is_same<T, __half>::value);
-      if (epi_kind == EPI_LSTM) {
-        const char* ev = getenv("DSB_LSTM_2CTA");      // opt-in while the CTA-pair kernel is being validated
-        st.pair = ev && ev[0] == '1';
-        encode_map_16(&st.b_half, W.w, W.N, W.Ktot, W.Ktot, 128, BK, std::is_same<T, __half>::value);
-      }
     }
     plan.steps.push_back(st);
   }
@@ -230,12 +208,15 @@ struct Builder {
   }
 
   void build() {
+    const dsb_plan_options& opt = ctx->opts;
     const int S = fm.signal_len, KL = fm.kmer_len;
     const int L2 = fm.L2, L3 = fm.L3, L4 = fm.L4;
     const int Lp2 = L2 + HALO, Lp3 = L3 + HALO, Lp4 = L4 + HALO;
+    (void)Lp3; (void)Lp4;
     const int64_t R2 = cap * Lp2;
     void* final_y = nullptr;
     int final_Lp = Lp4;
+    long long final_lo = 0;
 
     if (fm.has_cnn()) {
       // ---- device weights ----
@@ -247,45 +228,41 @@ struct Builder {
       }
       DevGemm<T> Wc2 = upload_gemm<T>(wa, fm.conv2, kparts({{0, 64}}, 64), up_stream);
       DevGemm<T> Wc3 = upload_gemm<T>(wa, fm.conv3, tap_parts(3, 128, 64), up_stream);
-      // ---- buffers ----
-      T* P1 = buf((size_t)R2 * 64);
-      T* C2 = buf((size_t)R2 * 128);
-      T* X0 = buf((size_t)R2 * 256);
-      T* X0_main = X0;
-      T* XP = buf((size_t)R2 * 256);
+      // ---- buffers (split mode: every matrix is followed by its lo twin) ----
       constexpr int YLD = 256;            // 240 channels padded to a 512-byte row pitch: every TMA row chunk is one aligned 128-byte line
-      T* YA = buf((size_t)R2 * YLD);
-      T* YB = buf((size_t)R2 * YLD);
-      T* TP3 = buf((size_t)R2 * 32);      // fused path: the block's 1x1 outputs as separate planes (contiguous TMA boxes)
-      T* TP4 = buf((size_t)R2 * 32);
-      T* TP5 = buf((size_t)R2 * 32);
-      T* TPS = buf((size_t)R2 * 48);
-      T* Tb = buf((size_t)R2 * 144);
-      T* Ub = buf((size_t)R2 * 64);
+      const size_t eP1 = (size_t)R2 * 64, eC2 = (size_t)R2 * 128, eX = (size_t)R2 * 256, eY = (size_t)R2 * YLD;
+      const size_t e32 = (size_t)R2 * 32, e48 = (size_t)R2 * 48, eT = (size_t)R2 * 144, eU = (size_t)R2 * 64;
+      T* P1 = abuf(eP1);
+      T* C2 = abuf(eC2);
+      T* X0 = abuf(eX);
+      T* XP = abuf(eX);
+      T* YA = abuf(eY);
+      T* YB = abuf(eY);
+      T* TP3 = abuf(e32);                 // fused path: the block's 1x1 outputs as separate planes (contiguous TMA boxes)
+      T* TP4 = abuf(e32);
+      T* TP5 = abuf(e32);
+      T* TPS = abuf(e48);
+      T* Tb = abuf(eT);
+      T* Ub = abuf(eU);
+      const long long loP1 = lo_of(eP1), loC2 = lo_of(eC2), loX = lo_of(eX), loY = lo_of(eY), lo32 = lo_of(e32), lo48 = lo_of(e48),
+                      loT = lo_of(eT), loU = lo_of(eU);
 
-      if (place) {
-        plan.dbg = {{"P1", {P1, (size_t)R2 * 64}}, {"C2", {C2, (size_t)R2 * 128}}, {"X0", {X0, (size_t)R2 * 256}}, {"YA", {YA, (size_t)R2 * YLD}}, {"YB", {YB, (size_t)R2 * YLD}},
-                    {"TP3", {TP3, (size_t)R2 * 32}}, {"TP4", {TP4, (size_t)R2 * 32}}, {"TP5", {TP5, (size_t)R2 * 32}}, {"TPS", {TPS, (size_t)R2 * 48}}};
-      }
-      auto conv_epi = [&](void* d0, int ld0, int c0, uint32_t relu, int Lp, int L) {
+      auto conv_epi = [&](void* d0, int ld0, int c0, uint32_t relu, int Lp, int L, long long lo0) {
         EpiParams e;
-        e.d0 = d0; e.ld0 = ld0; e.c0 = c0; e.split = 1 << 30; e.relu_mask = relu; e.Lp = Lp; e.L = L;
+        e.d0 = d0; e.ld0 = ld0; e.c0 = c0; e.split = 1 << 30; e.relu_mask = relu; e.Lp = Lp; e.L = L; e.lo_off0 = lo0;
         return e;
       };
       const int conv_total = std::max((fm.L1 - 1) * 2 + 7 - S, 0);
       const int pool_total = std::max((L2 - 1) * 2 + 3 - fm.L1, 0);
-      bool front = false;
-      if constexpr (TC) {
-        const char* ev = getenv("DSB_FRONT");        // DSB_FRONT=0 keeps stem_kernel + two GEMM launches (A/B tests)
-        front = !(ev && ev[0] == '0');
-      }
+      // the fused front end exists for the single 16-bit modes; the split mode runs the stem on the CUDA cores in fp32
+      // (exact hi + lo of its output) followed by conv2 / conv3 as generic GEMM launches
+      const bool front = TC && !SPLIT && opt.fused_front != 0;
       T* wB1 = reinterpret_cast<T*>(wa.take((size_t)192 * 64 * sizeof(T)));
       if (front) {
         if constexpr (TC) {
-          // conv1 + pool + conv2 + conv3 in one kernel (front_tc.cu): P1 and C2 stay in shared memory
+          // conv1 + pool + conv2 + conv3 in one kernel (front2_tc.cu): P1 and C2 stay in shared memory
           Step st;
           st.kind = ST_FRONT;
-          { const char* ev = getenv("DSB_FRONT"); st.front_cc = ev && ev[0] == '1'; }
           st.stream = 0;
           st.rows_per_sample = Lp2;
           st.kclass = KC_GEMM;
@@ -300,7 +277,7 @@ struct Builder {
             Q.p.S = S; Q.p.w1 = w1; Q.p.b1 = b1; Q.p.b2 = Wc2.bias; Q.p.b3 = Wc3.bias;
             Q.p.L1 = fm.L1; Q.p.L = L2; Q.p.Lp = Lp2; Q.p.conv_pl = conv_total / 2; Q.p.pool_pl = pool_total / 2;
             Q.p.X0 = X0; Q.p.ldX = 256;
-            // front2: conv1 as a 16-bit (hi | hi | lo) x (hi | lo | hi) MMA -- weights of channel c shifted to pool tap a in row a*64+c
+            // conv1 as a 16-bit (hi | hi | lo) x (hi | lo | hi) MMA -- weights of channel c shifted to pool tap a in row a*64+c
             std::vector<__half> hB1((size_t)192 * 64, __float2half_rn(0.f));     // fp16 parts in both precision modes
             for (int a = 0; a < 3; ++a)
               for (int c = 0; c < 64; ++c)
@@ -321,34 +298,22 @@ struct Builder {
           }
           plan.steps.push_back(st);
         }
-      }
-      const bool front_check = getenv("DSB_FRONT_CHECK") != nullptr;
-      T* X0ref = front_check ? buf((size_t)R2 * 256) : nullptr;
-      if (place && front_check) plan.dbg.push_back({"X0ref", {X0ref, (size_t)R2 * 256}});
-      if (!front || front_check) {
-        T* X0 = front_check ? X0ref : X0_main;
+      } else {
         {
           Step st;
           st.kind = ST_STEM;
           st.stream = 0;
-          st.stem = StemParams{nullptr, S, w1, b1, fm.L1, L2, Lp2, conv_total / 2, pool_total / 2, P1, 0};
+          st.stem = StemParams{nullptr, S, w1, b1, fm.L1, L2, Lp2, conv_total / 2, pool_total / 2, P1, 0, loP1};
           plan.steps.push_back(st);
         }
-        gemm(0, Lp2, R2, {SegHost{P1, 64, 64, 0, 0, 64, Lp2}}, Wc2, 64, conv_epi(C2, 128, 0, 0xffffffffu, Lp2, L2), EPI_CONV, KC_GEMM, L2, 64);
-        gemm(0, Lp2, R2, {SegHost{C2, 128, 128, 0, -1, 128, Lp2}, SegHost{C2, 128, 128, 0, 0, 128, Lp2}, SegHost{C2, 128, 128, 0, 1, 128, Lp2}},
-             Wc3, 64, conv_epi(X0, 256, 0, 0xffffffffu, Lp2, L2), EPI_CONV, KC_GEMM, L2, 384);
-        if (front_check) {
-          Step st;
-          st.kind = ST_DEBUG_CMP;
-          st.stream = 0;
-          st.rows_per_sample = Lp2;
-          st.src = X0_main; st.dst = X0ref; st.C = 192; st.ld = 256; st.Lpin = Lp2;
-          plan.steps.push_back(st);
-        }
+        gemm(0, Lp2, R2, {SegHost{P1, 64, 64, 0, 0, 64, Lp2, loP1}}, Wc2, 64, conv_epi(C2, 128, 0, 0xffffffffu, Lp2, L2, loC2), EPI_CONV, KC_GEMM, L2, 64);
+        gemm(0, Lp2, R2, {SegHost{C2, 128, 128, 0, -1, 128, Lp2, loC2}, SegHost{C2, 128, 128, 0, 0, 128, Lp2, loC2}, SegHost{C2, 128, 128, 0, 1, 128, Lp2, loC2}},
+             Wc3, 64, conv_epi(X0, 256, 0, 0xffffffffu, Lp2, L2, loX), EPI_CONV, KC_GEMM, L2, 384);
       }
 
       const T* X = X0;
       int xld = 256;
+      long long xlo = loX;
       int L = L2, Lp = Lp2;
       T* Y = YA;
       for (int i = 0; i < NBLOCK; ++i) {
@@ -361,11 +326,7 @@ struct Builder {
         DevGemm<T> Wb4 = upload_gemm<T>(wa, fb.b4, tap_parts(5, 32, 32), up_stream);
         DevGemm<T> Wb5b = upload_gemm<T>(wa, fb.b5b, tap_parts(3, 32, 32), up_stream);
         DevGemm<T> Wb5c = upload_gemm<T>(wa, fb.b5c, kparts({{0, 64}}, 64), up_stream);
-        bool fused = false;
-        if constexpr (TC) {
-          const char* ev = getenv("DSB_FUSED");       // DSB_FUSED=0 keeps the seven separate launches (debug / A-B tests)
-          fused = !(ev && ev[0] == '0');
-        }
+        const bool fused = TC && opt.fused_blocks != 0;
         if (fused) {
           if constexpr (TC) {
             const bool f16 = std::is_same<T, __half>::value;
@@ -373,7 +334,6 @@ struct Builder {
             float* biasA = reinterpret_cast<float*>(wa.take(240 * sizeof(float)));
             float* biasB = reinterpret_cast<float*>(wa.take(208 * sizeof(float)));
             Step sa, sb;
-            { const char* ev = getenv("DSB_A_PAIR"); sa.a_pair = ev && ev[0] == '1'; }
             sa.kind = ST_INCEPT_A; sa.stream = 0; sa.rows_per_sample = Lp; sa.kclass = KC_INCEPT_A;
             sb.kind = ST_INCEPT_B; sb.stream = 0; sb.rows_per_sample = Lp; sb.kclass = KC_GEMM;
             sa.flops_per_row = 2.0 * (double)cin * 240.0 * (double)L / (double)Lp;
@@ -389,6 +349,7 @@ struct Builder {
               DSB_CUDA(cudaStreamSynchronize(up_stream));
               InceptALaunch& A = sa.ia;
               A.fp16 = f16;
+              A.split = SPLIT;
               encode_map_16(&A.maps.x, X, rows_cap, cin, xld, 128, 64, f16);
               encode_map_16(&A.maps.wp1, Wp1.w, 192, Wp1.Ktot, Wp1.Ktot, 192, 64, f16);
               encode_map_16(&A.maps.wb1, Wb1.w, 48, Wb1.Ktot, Wb1.Ktot, 48, 64, f16);
@@ -397,13 +358,20 @@ struct Builder {
               encode_map_16(&A.maps.p4s, TP4, rows_cap, 32, 32, 32, 32, f16);
               encode_map_16(&A.maps.p5s, TP5, rows_cap, 32, 32, 32, 32, f16);
               encode_map_16(&A.maps.pss, TPS, rows_cap, 48, 48, 32, 32, f16);
-              A.maps2 = A.maps;
-              encode_map_16(&A.maps2.wp1, Wp1.w, 192, Wp1.Ktot, Wp1.Ktot, 96, 64, f16);
-              encode_map_16(&A.maps2.wb1, Wb1.w, 48, Wb1.Ktot, Wb1.Ktot, 24, 64, f16);
+              if (SPLIT) {
+                encode_map_16(&A.maps.xl, X + xlo, rows_cap, cin, xld, 128, 64, f16);
+                encode_map_16(&A.maps.ysl, Y + loY, rows_cap, CH, YLD, 32, 32, f16);
+                encode_map_16(&A.maps.p3sl, TP3 + lo32, rows_cap, 32, 32, 32, 32, f16);
+                encode_map_16(&A.maps.p4sl, TP4 + lo32, rows_cap, 32, 32, 32, 32, f16);
+                encode_map_16(&A.maps.p5sl, TP5 + lo32, rows_cap, 32, 32, 32, 32, f16);
+                encode_map_16(&A.maps.pssl, TPS + lo48, rows_cap, 48, 48, 32, 32, f16);
+                A.p.lo_y = loY; A.p.lo_p3 = A.p.lo_p4 = A.p.lo_p5 = lo32; A.p.lo_ps = lo48;
+              }
               for (int k = 0; k < 240; ++k) A.p.biasv[k] = ha[k];
               A.p.Lp = Lp; A.p.L = L; A.p.Y = Y; A.p.ldY = YLD; A.p.P3 = TP3; A.p.P4 = TP4; A.p.P5 = TP5; A.p.PS = TPS; A.p.bias = biasA;
               InceptBLaunch& B = sb.ib;
               B.fp16 = f16;
+              B.split = SPLIT;
               encode_map_16(&B.maps.t3, TP3, rows_cap, 32, 32, 136, 32, f16);      // 136-row boxes: taps are row-shifted
               encode_map_16(&B.maps.t4, TP4, rows_cap, 32, 32, 136, 32, f16);      // descriptors on one staged tile
               encode_map_16(&B.maps.t5, TP5, rows_cap, 32, 32, 136, 32, f16);
@@ -412,52 +380,51 @@ struct Builder {
               encode_map_16(&B.maps.w5b, Wb5b.w, 64, Wb5b.Ktot, Wb5b.Ktot, 64, 32, f16);
               encode_map_16(&B.maps.w5c, Wb5c.w, 48, Wb5c.Ktot, Wb5c.Ktot, 48, 32, f16);
               encode_map_16(&B.maps.ys, Y, rows_cap, CH, YLD, 32, 32, f16);               // epilogue TMA stores
+              if (SPLIT) {
+                encode_map_16(&B.maps.t3l, TP3 + lo32, rows_cap, 32, 32, 136, 32, f16);
+                encode_map_16(&B.maps.t4l, TP4 + lo32, rows_cap, 32, 32, 136, 32, f16);
+                encode_map_16(&B.maps.t5l, TP5 + lo32, rows_cap, 32, 32, 136, 32, f16);
+                encode_map_16(&B.maps.ysl, Y + loY, rows_cap, CH, YLD, 32, 32, f16);
+                B.p.lo_ps = lo48;
+              }
               for (int k = 0; k < 208; ++k) B.p.biasv[k] = hb[k];
               B.p.Lp = Lp; B.p.L = L; B.p.PS = TPS; B.p.Y = Y; B.p.ldY = YLD; B.p.bias = biasB;
             }
-            const char* fev = getenv("DSB_AB_FUSED");
-            if (fev && fev[0] == '1') {
-              Step sf;
-              sf.kind = ST_INCEPT_F; sf.stream = 0; sf.rows_per_sample = Lp; sf.kclass = KC_INCEPT_A;
-              sf.flops_per_row = sa.flops_per_row + sb.flops_per_row;
-              if (place) sf.fused_ab = std::shared_ptr<void>(make_incept_f(sa.ia, sb.ib, sa.ia.maps2.wp1, sa.ia.maps.wb1), free_incept_f);
-              plan.steps.push_back(sf);
-            } else {
-              plan.steps.push_back(sa);
-              plan.steps.push_back(sb);
-            }
+            plan.steps.push_back(sa);
+            plan.steps.push_back(sb);
           }
         } else {
-        {   // branch-1 max pool (1x3, stride 1)
+          {   // branch-1 max pool (1x3, stride 1)
             Step st;
             st.kind = ST_POOL1;
             st.stream = 0;
             st.rows_per_sample = Lp;
-            st.src = X; st.dst = XP; st.C = cin; st.ld = xld;
+            st.src = X; st.dst = XP; st.C = cin; st.ld = xld; st.lo_in = xlo; st.lo_out = loX;
             plan.steps.push_back(st);
           }
-          gemm(0, Lp, rows_cap, {SegHost{XP, xld, cin, 0, 0, cin, Lp}}, Wb1, 64, conv_epi(Y, YLD, 0, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, cin);
+          gemm(0, Lp, rows_cap, {SegHost{XP, xld, cin, 0, 0, cin, Lp, loX}}, Wb1, 64, conv_epi(Y, YLD, 0, 0xffffffffu, Lp, L, loY), EPI_CONV, KC_GEMM, L, cin);
           {   // fused 1x1s: b2 -> Y[:,48:96] ; b3a|b4a|b5a|stem -> T[:,0:144] (stem without ReLU)
-            EpiParams e = conv_epi(Y, YLD, 48, 0x1ffu /* cols 0..143 */, Lp, L);
+            EpiParams e = conv_epi(Y, YLD, 48, 0x1ffu /* cols 0..143 */, Lp, L, loY);
             e.split = 48;
-            e.d1 = Tb; e.ld1 = 144; e.c1 = 0;
-            gemm(0, Lp, rows_cap, {SegHost{X, xld, cin, 0, 0, cin, Lp}}, Wp1, 64, e, EPI_CONV, KC_GEMM, L, cin);
+            e.d1 = Tb; e.ld1 = 144; e.c1 = 0; e.lo_off1 = loT;
+            gemm(0, Lp, rows_cap, {SegHost{X, xld, cin, 0, 0, cin, Lp, xlo}}, Wp1, 64, e, EPI_CONV, KC_GEMM, L, cin);
           }
-          gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 0, -1, 32, Lp}, SegHost{Tb, 144, 144, 0, 0, 32, Lp}, SegHost{Tb, 144, 144, 0, 1, 32, Lp}},
-               Wb3, 32, conv_epi(Y, YLD, 96, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 96);
-          gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 32, -2, 32, Lp}, SegHost{Tb, 144, 144, 32, -1, 32, Lp}, SegHost{Tb, 144, 144, 32, 0, 32, Lp},
-                                 SegHost{Tb, 144, 144, 32, 1, 32, Lp}, SegHost{Tb, 144, 144, 32, 2, 32, Lp}},
-               Wb4, 32, conv_epi(Y, YLD, 144, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 160);
-          gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 64, -1, 32, Lp}, SegHost{Tb, 144, 144, 64, 0, 32, Lp}, SegHost{Tb, 144, 144, 64, 1, 32, Lp}},
-               Wb5b, 32, conv_epi(Ub, 64, 0, 0xffffffffu, Lp, L), EPI_CONV, KC_GEMM, L, 96);
+          gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 0, -1, 32, Lp, loT}, SegHost{Tb, 144, 144, 0, 0, 32, Lp, loT}, SegHost{Tb, 144, 144, 0, 1, 32, Lp, loT}},
+               Wb3, 32, conv_epi(Y, YLD, 96, 0xffffffffu, Lp, L, loY), EPI_CONV, KC_GEMM, L, 96);
+          gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 32, -2, 32, Lp, loT}, SegHost{Tb, 144, 144, 32, -1, 32, Lp, loT}, SegHost{Tb, 144, 144, 32, 0, 32, Lp, loT},
+                                 SegHost{Tb, 144, 144, 32, 1, 32, Lp, loT}, SegHost{Tb, 144, 144, 32, 2, 32, Lp, loT}},
+               Wb4, 32, conv_epi(Y, YLD, 144, 0xffffffffu, Lp, L, loY), EPI_CONV, KC_GEMM, L, 160);
+          gemm(0, Lp, rows_cap, {SegHost{Tb, 144, 144, 64, -1, 32, Lp, loT}, SegHost{Tb, 144, 144, 64, 0, 32, Lp, loT}, SegHost{Tb, 144, 144, 64, 1, 32, Lp, loT}},
+               Wb5b, 32, conv_epi(Ub, 64, 0, 0xffffffffu, Lp, L, loU), EPI_CONV, KC_GEMM, L, 96);
           {
-            EpiParams e = conv_epi(Y, YLD, 192, 0xffffffffu, Lp, L);
-            e.res = Tb; e.res_ld = 144; e.res_c0 = 96;
-            gemm(0, Lp, rows_cap, {SegHost{Ub, 64, 64, 0, 0, 64, Lp}}, Wb5c, 64, e, EPI_CONV, KC_GEMM, L, 64);
+            EpiParams e = conv_epi(Y, YLD, 192, 0xffffffffu, Lp, L, loY);
+            e.res = Tb; e.res_ld = 144; e.res_c0 = 96; e.res_lo_off = loT;
+            gemm(0, Lp, rows_cap, {SegHost{Ub, 64, 64, 0, 0, 64, Lp, loU}}, Wb5c, 64, e, EPI_CONV, KC_GEMM, L, 64);
           }
         }
         X = Y;
         xld = YLD;
+        xlo = loY;
         T* other = (Y == YA) ? YB : YA;
         if (i == 2 || i == 7) {   // max pool 1x3 stride 2 between stages
           const int Lo = (i == 2) ? L3 : L4, Lpo = Lo + HALO;
@@ -466,6 +433,7 @@ struct Builder {
           st.kind = ST_POOL2;
           st.stream = 0;
           st.src = Y; st.dst = other; st.C = CH; st.ld = YLD; st.Lin = L; st.Lpin = Lp; st.Lout = Lo; st.Lpout = Lpo; st.pl = total / 2;
+          st.lo_in = loY; st.lo_out = loY;
           plan.steps.push_back(st);
           X = other;
           other = Y;
@@ -475,6 +443,7 @@ struct Builder {
       }
       final_y = const_cast<T*>(X);
       final_Lp = Lp;
+      final_lo = xlo;
     }
 
     void* hfw = nullptr;
@@ -501,17 +470,12 @@ struct Builder {
               ? upload_gemm<T>(wa, fm.lstm[d][l].g, std::vector<std::array<int, 3>>{{0, HID, HID}, {HID, 8, FW}}, up_stream)
               : upload_gemm<T>(wa, fm.lstm[d][l].g, std::vector<std::array<int, 3>>{{0, HID, HID}, {HID, HID, HID}}, up_stream);
         }
-      bool seq = false;
-      if constexpr (TC) {
-        const char* ev = getenv("DSB_LSTM_SEQ");      // DSB_LSTM_SEQ=0 keeps one launch per (direction, layer, step) (A/B tests)
-        seq = !(ev && ev[0] == '0') && NLAYER == LSTM_SEQ_LAYERS;
-      }
+      const bool seq = TC && opt.lstm_seq != 0 && NLAYER == LSTM_SEQ_LAYERS;
       if (seq) {
         if constexpr (TC) {
-          // one persistent kernel for all directions, layers and time steps of the chunk (lstm_seq.cu)
+          // one persistent kernel for all directions, layers and time steps of the chunk (lstm_seq2.cu)
           Step st;
           st.kind = ST_LSTM_SEQ;
-          { const char* ev = getenv("DSB_LSTM_PAIR"); st.lstm_pair = !(ev && ev[0] == '0'); }
           st.stream = 1;
           st.rows_per_sample = 1;
           st.kclass = KC_LSTM;
@@ -525,7 +489,6 @@ struct Builder {
               Q.p.c[d] = Cst[d][0];
               for (int l = 0; l < NLAYER; ++l) {
                 encode_map_16(&Q.maps.h[d][l], H[d][l], (int64_t)(KL + 1) * cap, HID, HID, 128, 64, f16);
-                encode_map_16(&Q.maps.w[d][l], Wl[d][l].w, GATES, Wl[d][l].Ktot, Wl[d][l].Ktot, 256, 64, f16);
                 encode_map_16(&Q.maps.w2[d][l], Wl[d][l].w, GATES, Wl[d][l].Ktot, Wl[d][l].Ktot, 128, 64, f16);
                 Q.p.bias[d][l] = Wl[d][l].bias;
                 Q.p.H[d][l] = H[d][l];
@@ -585,18 +548,18 @@ struct Builder {
       Step st;
       st.kind = ST_HEAD;
       st.stream = 0;
-      st.head = HeadParams{final_y, final_Lp, fm.L4, 256, hfw, hbw, Wc, Wr, nullptr, nullptr, 0};
+      st.head = HeadParams{final_y, final_Lp, fm.L4, 256, hfw, hbw, Wc, Wr, nullptr, nullptr, 0, final_lo, ctx->nonfinite_dev};
       plan.steps.push_back(st);
     }
   }
 };
 
-template <class T>
+template <class T, bool SPLIT>
 void build_plan(dsb_ctx* ctx, ForwardPlan& plan, int64_t cap, cudaStream_t s) {
   // pass 1: sizes
   {
     ForwardPlan scratch;
-    Builder<T> b{ctx, scratch, ctx->model, cap, Arena{}, Arena{}, false, s};
+    Builder<T, SPLIT> b{ctx, scratch, ctx->model, cap, Arena{}, Arena{}, false, s};
     b.build();
     plan.weights.ensure(b.wa.off + 1024);
     plan.work.ensure(b.ba.off + 1024);
@@ -607,7 +570,7 @@ void build_plan(dsb_ctx* ctx, ForwardPlan& plan, int64_t cap, cudaStream_t s) {
   Arena wa, ba;
   wa.base = reinterpret_cast<uint8_t*>(plan.weights.p);
   ba.base = reinterpret_cast<uint8_t*>(plan.work.p);
-  Builder<T> b{ctx, plan, ctx->model, cap, wa, ba, true, s};
+  Builder<T, SPLIT> b{ctx, plan, ctx->model, cap, wa, ba, true, s};
   b.build();
   DSB_CUDA(cudaStreamSynchronize(s));
   plan.cap = cap;
@@ -633,43 +596,18 @@ struct Timer {       // optional CUDA-event bracket around one launch
   }
 };
 
-template <class T>
+template <class T, bool SPLIT>
 void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, const float* means, const float* stds,
                const float* lens, const float* signals, float* probs, int32_t* pred, cudaStream_t main_stream) {
   const FoldedModel& fm = ctx->model;
   const bool multi = plan.multi_stream && !ctx->prof.enabled && fm.has_rnn() && fm.has_cnn();
   cudaStream_t streams[3] = {main_stream, multi ? plan.side[0] : main_stream, multi ? plan.side[1] : main_stream};
-  // SM budget per stream: the persistent kernels size their grids to it, so the LSTM stream (L2-bound) and the
-  // CNN stream (HBM-bound) can run side by side instead of time-slicing whole-GPU grids.
-  static const int lstm_sms_env = getenv("DSB_LSTM_SMS") ? atoi(getenv("DSB_LSTM_SMS")) : 0;
-  int sms[3] = {ctx->sm_count, ctx->sm_count, ctx->sm_count};
-  if (multi && lstm_sms_env > 0 && lstm_sms_env < ctx->sm_count / 2) {
-    sms[1] = sms[2] = lstm_sms_env;
-    sms[0] = ctx->sm_count - 2 * lstm_sms_env;
-  }
+  // every persistent kernel sizes its grid to the whole GPU; the LSTM stream (L2 / tensor bound) and the CNN stream
+  // (HBM bound) time-slice the SMs (partitioning them measured slower: profiles/r1_ablation.md)
+  const int sms[3] = {ctx->sm_count, ctx->sm_count, ctx->sm_count};
+  const dsb_plan_options& opt = ctx->opts;
   bool forked = false;
-  static const bool debug_sync = getenv("DSB_DEBUG_SYNC") != nullptr;
-  int step_idx = -1;
   for (const Step& st : plan.steps) {
-    ++step_idx;
-    if (debug_sync && step_idx > 0) {
-      cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) fail(DSB_ERR_CUDA, "step %d (kind %d) failed: %s", step_idx - 1, plan.steps[step_idx - 1].kind, cudaGetErrorString(e));
-      if (getenv("DSB_DEBUG_SUM")) {
-        unsigned long long* d = nullptr;
-        cudaMalloc(&d, 8);
-        fprintf(stderr, "[sum] after step %d kind %d:", step_idx - 1, plan.steps[step_idx - 1].kind);
-        for (auto& b : plan.dbg) {
-          cudaMemset(d, 0, 8);
-          debug_sum_kernel<<<256, 256>>>(reinterpret_cast<const uint16_t*>(b.second.first), (long long)b.second.second, d);
-          unsigned long long h = 0;
-          cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-          fprintf(stderr, " %s=%llx", b.first, h);
-        }
-        fprintf(stderr, "\n");
-        cudaFree(d);
-      }
-    }
     cudaStream_t s = streams[st.stream];
     if (multi && !forked && st.kind != ST_FEAT) {
       // everything after the feature rows may run on the three streams concurrently
@@ -688,8 +626,7 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
           g.rows_valid = (int)M;
           launch_gemm_f32(g, st.epi_kind, s);
         } else {
-          if (st.pair) launch_gemm_tc2_lstm(st.tc, st.b_half, (int)M, sms[st.stream], s);
-          else launch_gemm_tc(st.tc, (int)M, sms[st.stream], s);
+          launch_gemm_tc(st.tc, (int)M, sms[st.stream], opt.ablate_gemm, s);
         }
         ctx->launches++;
         break;
@@ -697,16 +634,7 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_INCEPT_A: {
         if constexpr (!std::is_same<T, float>::value) {
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
-          if (st.a_pair) launch_incept_a2(st.ia, (int)M, sms[st.stream], s);
-          else launch_incept_a(st.ia, (int)M, sms[st.stream], s);
-          ctx->launches++;
-        }
-        break;
-      }
-      case ST_INCEPT_F: {
-        if constexpr (!std::is_same<T, float>::value) {
-          Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
-          launch_incept_f(st.fused_ab.get(), (int)M, sms[st.stream], s);
+          launch_incept_a(st.ia, (int)M, sms[st.stream], opt.ablate_a, s);
           ctx->launches++;
         }
         break;
@@ -714,7 +642,7 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_INCEPT_B: {
         if constexpr (!std::is_same<T, float>::value) {
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
-          launch_incept_b(st.ib, (int)M, sms[st.stream], s);
+          launch_incept_b(st.ib, (int)M, sms[st.stream], opt.ablate_b, s);
           ctx->launches++;
         }
         break;
@@ -722,8 +650,7 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_LSTM_SEQ: {
         if constexpr (!std::is_same<T, float>::value) {
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
-          if (st.lstm_pair) launch_lstm_seq2(st.seq, (int)n, sms[st.stream], s);
-          else launch_lstm_seq(st.seq, (int)n, sms[st.stream], s);
+          launch_lstm_seq2(st.seq, (int)n, sms[st.stream], opt.ablate_lstm, s);
           ctx->launches++;
         }
         break;
@@ -731,25 +658,9 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_FRONT: {
         if constexpr (!std::is_same<T, float>::value) {
           Timer tm(ctx, s, st.kclass, st.flops_per_row * (double)M);
-          if (st.front_cc) launch_front(st.front, signals, (int)n, sms[st.stream], s);
-          else launch_front2(st.front, signals, (int)n, sms[st.stream], s);
+          launch_front2(st.front, signals, (int)n, sms[st.stream], s);
           ctx->launches++;
         }
-        break;
-      }
-      case ST_DEBUG_CMP: {
-        int* cnt = nullptr;
-        DSB_CUDA(cudaMalloc(&cnt, sizeof(int)));
-        DSB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), s));
-        const long long rows_all = plan.cap * st.rows_per_sample;
-        const long long total = rows_all * 256;
-        debug_compare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint16_t*>(st.src), reinterpret_cast<const uint16_t*>(st.dst),
-                                                                            rows_all, 256, st.ld, st.Lpin, cnt);
-        int h = 0;
-        DSB_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
-        DSB_CUDA(cudaStreamSynchronize(s));
-        fprintf(stderr, "[front check] %d mismatching elements of %lld\n", h, total);
-        cudaFree(cnt);
         break;
       }
       case ST_STEM: {
@@ -766,7 +677,10 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_POOL1: {
         Timer tm(ctx, s, KC_ELEM, 0);
         const int64_t total = M * (st.C / 8);
-        pool3s1_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), M, st.C, st.ld);
+        if constexpr (SPLIT)
+          pool3s1_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __half*>(st.src), reinterpret_cast<__half*>(st.dst), M, st.C, st.ld, st.lo_in, st.lo_out);
+        else
+          pool3s1_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), M, st.C, st.ld);
         DSB_CUDA(cudaGetLastError());
         ctx->launches++;
         break;
@@ -774,8 +688,12 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_POOL2: {
         Timer tm(ctx, s, KC_ELEM, 0);
         const int64_t total = n * st.Lpout * (st.C / 8);
-        pool3s2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), n, st.C, st.ld,
-                                                                          st.Lin, st.Lpin, st.Lout, st.Lpout, st.pl);
+        if constexpr (SPLIT)
+          pool3s2_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __half*>(st.src), reinterpret_cast<__half*>(st.dst), n, st.C, st.ld,
+                                                                               st.Lin, st.Lpin, st.Lout, st.Lpout, st.pl, st.lo_in, st.lo_out);
+        else
+          pool3s2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), n, st.C, st.ld,
+                                                                            st.Lin, st.Lpin, st.Lout, st.Lpout, st.pl);
         DSB_CUDA(cudaGetLastError());
         ctx->launches++;
         break;
@@ -823,22 +741,23 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
 
 }  // namespace
 
+template <class T, bool SPLIT>
+size_t plan_bytes(const dsb_ctx* ctx, int64_t chunk) {
+  ForwardPlan scratch;
+  Builder<T, SPLIT> b{const_cast<dsb_ctx*>(ctx), scratch, ctx->model, chunk, Arena{}, Arena{}, false, nullptr};
+  b.build();
+  return b.ba.off + b.wa.off;
+}
+
 size_t forward_workspace_bytes(const dsb_ctx* ctx, int64_t chunk, int precision) {
   if (!ctx->have_model) return 0;
-  ForwardPlan scratch;
   size_t bytes = 0;
-  if (precision == DSB_PREC_FP32) {
-    Builder<float> b{const_cast<dsb_ctx*>(ctx), scratch, ctx->model, chunk, Arena{}, Arena{}, false, nullptr};
-    b.build();
-    bytes = b.ba.off + b.wa.off;
-  } else if (precision == DSB_PREC_FP16) {
-    Builder<__half> b{const_cast<dsb_ctx*>(ctx), scratch, ctx->model, chunk, Arena{}, Arena{}, false, nullptr};
-    b.build();
-    bytes = b.ba.off + b.wa.off;
-  } else {
-    Builder<__nv_bfloat16> b{const_cast<dsb_ctx*>(ctx), scratch, ctx->model, chunk, Arena{}, Arena{}, false, nullptr};
-    b.build();
-    bytes = b.ba.off + b.wa.off;
+  switch (precision) {
+    case DSB_PREC_FP32: bytes = plan_bytes<float, false>(ctx, chunk); break;
+    case DSB_PREC_FP16: bytes = plan_bytes<__half, false>(ctx, chunk); break;
+    case DSB_PREC_FP16X2: bytes = plan_bytes<__half, true>(ctx, chunk); break;
+    case DSB_PREC_BF16: bytes = plan_bytes<__nv_bfloat16, false>(ctx, chunk); break;
+    default: return 0;
   }
   return bytes + 2048;
 }
@@ -846,7 +765,7 @@ size_t forward_workspace_bytes(const dsb_ctx* ctx, int64_t chunk, int precision)
 void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, const float* means, const float* stds,
                  const float* lens, const float* signals, float* probs, int32_t* pred, cudaStream_t stream) {
   if (!ctx->have_model) fail(DSB_ERR_STATE, "dsb_forward called before dsb_load_weights");
-  if (precision != DSB_PREC_FP32 && precision != DSB_PREC_BF16 && precision != DSB_PREC_FP16) fail(DSB_ERR_INVALID, "unknown precision %d", precision);
+  if (precision < DSB_PREC_FP32 || precision > DSB_PREC_FP16X2) fail(DSB_ERR_INVALID, "unknown precision %d", precision);
   if (n < 0) fail(DSB_ERR_INVALID, "negative sample count");
   if (n == 0) return;
   if (!signals || !probs || !pred || (ctx->model.has_rnn() && (!means || !stds || !lens || (ctx->model.has_base() && !kmer))))
@@ -854,6 +773,10 @@ void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, co
   if (precision != DSB_PREC_FP32 && ctx->cc_major != 10)
     fail(DSB_ERR_ARCH, "the 16-bit tensor-core path needs an sm_100 device (found sm_%d%d); there is no fallback", ctx->cc_major, ctx->cc_minor);
   DSB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->nonfinite_dev) {
+    DSB_CUDA(cudaMalloc(&ctx->nonfinite_dev, sizeof(int)));
+    DSB_CUDA(cudaMemset(ctx->nonfinite_dev, 0, sizeof(int)));
+  }
   const int64_t want = std::min<int64_t>(ctx->max_chunk, (n + 127) / 128 * 128);
   auto& slot = ctx->plan[precision];
   if (!slot || slot->cap < want || slot->cap > ctx->max_chunk) {
@@ -865,9 +788,12 @@ void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, co
     DSB_CUDA(cudaEventCreateWithFlags(&np->ev_fork, cudaEventDisableTiming));
     DSB_CUDA(cudaEventCreateWithFlags(&np->ev_join[0], cudaEventDisableTiming));
     DSB_CUDA(cudaEventCreateWithFlags(&np->ev_join[1], cudaEventDisableTiming));
-    if (precision == DSB_PREC_FP32) build_plan<float>(ctx, *np, want, stream);
-    else if (precision == DSB_PREC_FP16) build_plan<__half>(ctx, *np, want, stream);
-    else build_plan<__nv_bfloat16>(ctx, *np, want, stream);
+    switch (precision) {
+      case DSB_PREC_FP32: build_plan<float, false>(ctx, *np, want, stream); break;
+      case DSB_PREC_FP16: build_plan<__half, false>(ctx, *np, want, stream); break;
+      case DSB_PREC_FP16X2: build_plan<__half, true>(ctx, *np, want, stream); break;
+      default: build_plan<__nv_bfloat16, false>(ctx, *np, want, stream); break;
+    }
     slot = std::move(np);
   }
   ForwardPlan& plan = *slot;
@@ -878,12 +804,15 @@ void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, co
     const float* mu = means ? means + off * KL : nullptr;
     const float* sd = stds ? stds + off * KL : nullptr;
     const float* ln = lens ? lens + off * KL : nullptr;
-    if (precision == DSB_PREC_FP32)
-      run_chunk<float>(ctx, plan, m, k, mu, sd, ln, signals + off * S, probs + off * 2, pred + off, stream);
-    else if (precision == DSB_PREC_FP16)
-      run_chunk<__half>(ctx, plan, m, k, mu, sd, ln, signals + off * S, probs + off * 2, pred + off, stream);
-    else
-      run_chunk<__nv_bfloat16>(ctx, plan, m, k, mu, sd, ln, signals + off * S, probs + off * 2, pred + off, stream);
+    const float* sg = signals + off * S;
+    float* pr = probs + off * 2;
+    int32_t* pd = pred + off;
+    switch (precision) {
+      case DSB_PREC_FP32: run_chunk<float, false>(ctx, plan, m, k, mu, sd, ln, sg, pr, pd, stream); break;
+      case DSB_PREC_FP16: run_chunk<__half, false>(ctx, plan, m, k, mu, sd, ln, sg, pr, pd, stream); break;
+      case DSB_PREC_FP16X2: run_chunk<__half, true>(ctx, plan, m, k, mu, sd, ln, sg, pr, pd, stream); break;
+      default: run_chunk<__nv_bfloat16, false>(ctx, plan, m, k, mu, sd, ln, sg, pr, pd, stream); break;
+    }
   }
 }
 

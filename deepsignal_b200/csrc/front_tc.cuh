@@ -33,7 +33,6 @@ struct FrontLaunch { FrontMaps maps; FrontParams p; bool fp16 = false; };
 
 constexpr int FRONT_TILE_ROWS = 126;   // 128-row tiles overlap by one row on each side (conv3 halo)
 
-void launch_front(const FrontLaunch& L, const float* signals, int n, int sm_count, cudaStream_t s);
 void launch_front2(const FrontLaunch& L, const float* signals, int n, int sm_count, cudaStream_t s);   // conv1 on the tensor cores too (front2_tc.cu)
 
 }  // namespace dsb

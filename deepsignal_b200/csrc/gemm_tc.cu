@@ -10,6 +10,7 @@
 // Accumulators are double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  A-operand "segments" give k-tap convs (row-shifted TMA boxes; out-of-range rows are
 // zero-filled by TMA, sample edges read the zero halo rows) and [x_t | h_{t-1}] for the LSTM.
+#include <algorithm>
 #include <cstdlib>
 
 #include "gemm_tc.cuh"
@@ -36,7 +37,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
   for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
   const uint32_t stage_bytes = resident ? a_bytes : a_bytes + b_bytes;
   const uint32_t bres_base = smem_base;                                   // resident B: total_kb blocks of b_bytes
-  const uint32_t ring_base = smem_base + (resident ? (uint32_t)total_kb * b_bytes : 0u);
+  const uint32_t ring_base = smem_base + (resident ? (uint32_t)p.wkb_total * b_bytes : 0u);
   const int stages = p.stages;
   const uint32_t bar_base = ring_base + stages * stage_bytes;   // 8-byte barriers
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -81,12 +82,11 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
       int stage = 0;
       uint32_t phase = 0;
       if (resident && t_begin < num_tiles) {
-        mbar_expect_tx(bres_bar, (uint32_t)total_kb * b_bytes);
-        for (int kb = 0; kb < total_kb; ++kb) tma_load_2d(bres_base + kb * b_bytes, &maps.b, bres_bar, kb * BK, my_n * BN);
+        mbar_expect_tx(bres_bar, (uint32_t)p.wkb_total * b_bytes);
+        for (int kb = 0; kb < p.wkb_total; ++kb) tma_load_2d(bres_base + kb * b_bytes, &maps.b, bres_bar, kb * BK, my_n * BN);
       }
       for (int tile = t_begin; tile < num_tiles; tile += t_step) {
         const int row0 = tile_m(tile) * BM_TC, n0 = tile_n(tile) * BN;
-        int kb_global = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const SegTC sg = p.seg[s];
           for (int j = 0; j < sg.nkb; ++j) {
@@ -94,8 +94,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
             mbar_expect_tx(full_bar(stage), stage_bytes);
             const uint32_t a_dst = ring_base + stage * stage_bytes;
             tma_load_2d(a_dst, &maps.a[sg.map], full_bar(stage), sg.col0 + j * BK, row0 + sg.drow);
-            if (!resident) tma_load_2d(a_dst + a_bytes, &maps.b, full_bar(stage), kb_global * BK, n0);
-            ++kb_global;
+            if (!resident) tma_load_2d(a_dst + a_bytes, &maps.b, full_bar(stage), (sg.wkb + j) * BK, n0);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -115,17 +114,21 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < total_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = ring_base + stage * stage_bytes;
-          const uint64_t adesc = make_kmajor_desc<BK>(a_addr);
-          const uint64_t bdesc = make_kmajor_desc<BK>(resident ? bres_base + kb * b_bytes : a_addr + a_bytes);
+        int kb = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int wkb0 = p.seg[s].wkb, nkb = p.seg[s].nkb;
+          for (int j = 0; j < nkb; ++j, ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_addr = ring_base + stage * stage_bytes;
+            const uint64_t adesc = make_kmajor_desc<BK>(a_addr);
+            const uint64_t bdesc = make_kmajor_desc<BK>(resident ? bres_base + (uint32_t)(wkb0 + j) * b_bytes : a_addr + a_bytes);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit(empty_bar(stage));
-          if (++stage == stages) { stage = 0; phase ^= 1u; }
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit(empty_bar(stage));
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
         }
         tc_commit(tfull_bar(acc));
         acc ^= 1;
@@ -189,6 +192,16 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
                   v[8 * h + 2 * i] += f.x;
                   v[8 * h + 2 * i + 1] += f.y;
                 }
+                if (e.res_lo_off != 0) {                   // split-operand mode: the residual is hi + lo
+                  const uint4 lv = __ldg(rp + h + e.res_lo_off / 8);
+                  const uint32_t wl[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = unpack16<F16>(wl[i]);
+                    v[8 * h + 2 * i] += f.x;
+                    v[8 * h + 2 * i + 1] += f.y;
+                  }
+                }
               }
             }
             if ((e.relu_mask >> (col >> 4)) & 1u) {
@@ -207,6 +220,18 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
               uint4* dp = reinterpret_cast<uint4*>(dst);
               dp[0] = make_uint4(pk[8 * h2 + 0], pk[8 * h2 + 1], pk[8 * h2 + 2], pk[8 * h2 + 3]);
               dp[1] = make_uint4(pk[8 * h2 + 4], pk[8 * h2 + 5], pk[8 * h2 + 6], pk[8 * h2 + 7]);
+              const long long lo_off = first ? e.lo_off0 : e.lo_off1;
+              if (lo_off != 0) {                           // lo = fp16(v - hi): the part of v the 16-bit value lost
+                uint32_t pl[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float2 hf = unpack16<F16>(pk[8 * h2 + i]);
+                  pl[i] = pack16<F16>(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+                }
+                uint4* lp = reinterpret_cast<uint4*>(dst + lo_off);
+                lp[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                lp[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+              }
             }
           }
           if (staged) {
@@ -297,7 +322,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 template <int BK, int EPI, bool F16>
-void launch_one(const TcLaunch& L, int m_tiles, int grid, uint32_t tmem_cols, cudaStream_t s) {
+void launch_one(const TcLaunch& L, int m_tiles, int grid, uint32_t tmem_cols, int ablate, cudaStream_t s) {
   auto kern = gemm_tc_kernel<BK, EPI, F16>;
   static bool configured[64] = {false};
   int dev = 0;
@@ -306,7 +331,6 @@ void launch_one(const TcLaunch& L, int m_tiles, int grid, uint32_t tmem_cols, cu
     DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[dev & 63] = true;
   }
-  static const int ablate = getenv("DSB_ABLATE_G") ? atoi(getenv("DSB_ABLATE_G")) : 0;   // timing experiments only
   launch_pdl(kern, grid, TC_THREADS, L.smem, s, L.maps, L.p, m_tiles, tmem_cols, ablate);
 }
 
@@ -332,8 +356,9 @@ void encode_map_16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
 void finalize_tc_launch(TcLaunch& L) {
   if (L.p.BN % 16 != 0 || L.p.BN < 16 || L.p.BN > 256 || L.p.epi.N % L.p.BN != 0)
     fail(DSB_ERR_INVALID, "bad GEMM tile: N=%d BN=%d", L.p.epi.N, L.p.BN);
-  int total_kb = 0;
-  for (int s = 0; s < L.p.nseg; ++s) total_kb += L.p.seg[s].nkb;
+  int total_kb = 0;                                   // weight blocks (segments may share them)
+  for (int s = 0; s < L.p.nseg; ++s) total_kb = std::max(total_kb, L.p.seg[s].wkb + L.p.seg[s].nkb);
+  L.p.wkb_total = total_kb;
   const size_t a_bytes = (size_t)BM_TC * L.BK * 2;
   const size_t budget = 196 * 1024;
   // conv weights are small: keep the whole [BN x K] operand in shared memory when it leaves room for >= 4 A stages
@@ -362,7 +387,7 @@ void finalize_tc_launch(TcLaunch& L) {
   L.smem = smem;
 }
 
-void launch_gemm_tc(const TcLaunch& L, int M, int sm_count, cudaStream_t s) {
+void launch_gemm_tc(const TcLaunch& L, int M, int sm_count, int ablate, cudaStream_t s) {
   const int m_tiles = (M + BM_TC - 1) / BM_TC;
   const int ntn = L.p.epi.N / L.p.BN;
   const int num_tiles = m_tiles * ntn;
@@ -376,12 +401,12 @@ void launch_gemm_tc(const TcLaunch& L, int M, int sm_count, cudaStream_t s) {
   Lr.p.epi.M = M;
   const int key = (L.BK == 64 ? 0 : 4) | (L.epi_kind == EPI_CONV ? 0 : 2) | (L.fp16 ? 1 : 0);
   switch (key) {
-    case 0: launch_one<64, EPI_CONV, false>(Lr, m_tiles, grid, cols, s); break;
-    case 1: launch_one<64, EPI_CONV, true>(Lr, m_tiles, grid, cols, s); break;
-    case 2: launch_one<64, EPI_LSTM, false>(Lr, m_tiles, grid, cols, s); break;
-    case 3: launch_one<64, EPI_LSTM, true>(Lr, m_tiles, grid, cols, s); break;
-    case 4: launch_one<32, EPI_CONV, false>(Lr, m_tiles, grid, cols, s); break;
-    case 5: launch_one<32, EPI_CONV, true>(Lr, m_tiles, grid, cols, s); break;
+    case 0: launch_one<64, EPI_CONV, false>(Lr, m_tiles, grid, cols, ablate, s); break;
+    case 1: launch_one<64, EPI_CONV, true>(Lr, m_tiles, grid, cols, ablate, s); break;
+    case 2: launch_one<64, EPI_LSTM, false>(Lr, m_tiles, grid, cols, ablate, s); break;
+    case 3: launch_one<64, EPI_LSTM, true>(Lr, m_tiles, grid, cols, ablate, s); break;
+    case 4: launch_one<32, EPI_CONV, false>(Lr, m_tiles, grid, cols, ablate, s); break;
+    case 5: launch_one<32, EPI_CONV, true>(Lr, m_tiles, grid, cols, ablate, s); break;
     default: fail(DSB_ERR_INVALID, "LSTM epilogue needs BK=64");
   }
 }

@@ -9,6 +9,8 @@ struct SegTC {            // one A segment: K blocks read through tensor map `ma
   int col0;               // first column (elements) in the mapped matrix
   int drow;               // row shift (conv tap - pad)
   int nkb;                // number of BK-wide K blocks
+  int wkb;                // first BK-wide block of the weight matrix this segment multiplies (the hi and lo parts of an
+                          // activation share their weight blocks in the split-operand mode)
 };
 
 struct alignas(64) TcMaps {
@@ -22,6 +24,7 @@ struct GemmTCParams {
   int BN = 0;             // N tile (multiple of 16, <= 256, divides epi.N)
   int stages = 0;
   int resident = 0;       // 1: the CTA's whole B tile [BN x K] is loaded once and stays in smem (conv weights)
+  int wkb_total = 0;      // BK-wide blocks of the weight matrix (= sum of nkb unless segments share weight blocks)
   EpiParams epi;
 };
 
@@ -40,8 +43,6 @@ struct TcLaunch {         // everything needed to launch one prebuilt GEMM
 void encode_map_16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
                    int box_rows, int box_cols, bool fp16);
 void finalize_tc_launch(TcLaunch& L);                       // picks stages / smem
-void launch_gemm_tc(const TcLaunch& L, int M, int sm_count, cudaStream_t s);
-// CTA-pair (tcgen05 cta_group::2) variant of the LSTM step GEMM; b_half = weights map with a 128-row box.
-void launch_gemm_tc2_lstm(const TcLaunch& L, const CUtensorMap& b_half, int M, int sm_count, cudaStream_t s);
+void launch_gemm_tc(const TcLaunch& L, int M, int sm_count, int ablate, cudaStream_t s);
 
 }  // namespace dsb

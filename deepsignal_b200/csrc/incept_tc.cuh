@@ -13,7 +13,12 @@
 
 namespace dsb {
 
-struct alignas(64) InceptAMaps { CUtensorMap x, wp1, wb1, ys, p3s, p4s, p5s, pss; };   // *s: [32 x 32] store boxes over Y and the planes
+// Split-operand mode (DSB_PREC_FP16X2): every activation matrix has a lo twin (v = hi + lo, both fp16); the *l maps address
+// the twins.  The weights stay single fp16: [xh | xl] · [W ; W] re-uses each weight block for both parts.
+struct alignas(64) InceptAMaps {
+  CUtensorMap x, wp1, wb1, ys, p3s, p4s, p5s, pss;      // *s: [32 x 32] store boxes over Y and the planes
+  CUtensorMap xl, ysl, p3sl, p4sl, p5sl, pssl;          // lo twins (split mode only)
+};
 struct InceptAParams {
   int M = 0, Lp = 0, L = 0;
   int nkb = 4;                 // 64-wide K blocks of the input channels (256 or 240 -> 4)
@@ -23,10 +28,14 @@ struct InceptAParams {
   int ablate = 0;              // timing experiments only (DSB_ABLATE_A): 1 skip pool math, 2 skip epilogue stores
   const float* bias = nullptr; // [240]: b1 (48) then p1 (b2 48 | b3a 32 | b4a 32 | b5a 32 | stem 48)
   float biasv[240];            // the same values by value: read through the constant bank (LDC), not shared memory
+  long long lo_y = 0, lo_p3 = 0, lo_p4 = 0, lo_p5 = 0, lo_ps = 0;   // element offsets hi -> lo twin (split mode)
 };
-struct InceptALaunch { InceptAMaps maps; InceptAMaps maps2; InceptAParams p; bool fp16 = false; };   // maps2: weight maps with half-height boxes (CTA-pair kernel)
+struct InceptALaunch { InceptAMaps maps; InceptAParams p; bool fp16 = false; bool split = false; };
 
-struct alignas(64) InceptBMaps { CUtensorMap t3, t4, t5, w3, w4, w5b, w5c, ys; };   // ys: Y as [32 x 32] store boxes
+struct alignas(64) InceptBMaps {
+  CUtensorMap t3, t4, t5, w3, w4, w5b, w5c, ys;         // ys: Y as [32 x 32] store boxes
+  CUtensorMap t3l, t4l, t5l, ysl;                       // lo twins (split mode only)
+};
 struct InceptBParams {
   int M = 0, Lp = 0, L = 0;
   const void* PS = nullptr;    // [M][48] residual stem plane
@@ -34,17 +43,14 @@ struct InceptBParams {
   int ablate = 0;              // timing experiments only (DSB_ABLATE_B): 1 skip staging math, 2 skip epilogue stores
   const float* bias = nullptr; // [208]: b3 48 | b4 48 | b5c 48 | b5b 64
   float biasv[208];            // by value: constant-bank reads keep the bias off the shared-memory data pipe
+  long long lo_ps = 0;         // element offset PS -> its lo twin (split mode)
 };
-struct InceptBLaunch { InceptBMaps maps; InceptBParams p; bool fp16 = false; };
+struct InceptBLaunch { InceptBMaps maps; InceptBParams p; bool fp16 = false; bool split = false; };
 
 constexpr int INCEPT_A_TILE_ROWS = 126;   // 128-row tiles overlap by one row on each side (pool halo)
 
-void launch_incept_a(const InceptALaunch& L, int M, int sm_count, cudaStream_t s);
-void launch_incept_b(const InceptBLaunch& L, int M, int sm_count, cudaStream_t s);
-void launch_incept_a2(const InceptALaunch& L, int M, int sm_count, cudaStream_t s);   // CTA-pair variant of kernel A (incept_a2.cu)
-// single-kernel inception block (incept_f.cu, opt-in): built from the A / B launch descriptions of the same block
-void* make_incept_f(const InceptALaunch& A, const InceptBLaunch& B, const CUtensorMap& wp1_half, const CUtensorMap& wb1_full);
-void free_incept_f(void* h);
-void launch_incept_f(const void* h, int M, int sm_count, cudaStream_t s);
+// ablate: timing experiments only (dsb_plan_options): 1 skip pool / staging math, 2 skip epilogue stores
+void launch_incept_a(const InceptALaunch& L, int M, int sm_count, int ablate, cudaStream_t s);
+void launch_incept_b(const InceptBLaunch& L, int M, int sm_count, int ablate, cudaStream_t s);
 
 }  // namespace dsb

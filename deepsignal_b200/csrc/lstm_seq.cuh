@@ -9,8 +9,7 @@ constexpr int LSTM_SEQ_LAYERS = 3;
 struct alignas(64) LstmSeqMaps {
   CUtensorMap f;                          // layer-0 feature rows F [KL*cap][FW], box 128 x 64
   CUtensorMap h[2][LSTM_SEQ_LAYERS];      // H[dir][layer] [(KL+1)*cap][256], box 128 x 64 (slot t+1 = output of step t)
-  CUtensorMap w[2][LSTM_SEQ_LAYERS];      // gate weights [1024][Ktot] (columns 4*u+g), box 256 x 64
-  CUtensorMap w2[2][LSTM_SEQ_LAYERS];     // the same weights with a 128-row box (CTA-pair kernel: half a block per CTA)
+  CUtensorMap w2[2][LSTM_SEQ_LAYERS];     // gate weights [1024][Ktot] (columns 4*u+g), 128-row box: half a 256-row block per CTA of a pair
 };
 
 struct LstmSeqParams {
@@ -29,7 +28,7 @@ struct LstmSeqLaunch {
   double flops_per_sample = 0;
 };
 
-void launch_lstm_seq(const LstmSeqLaunch& L, int n, int sm_count, cudaStream_t s);
-void launch_lstm_seq2(const LstmSeqLaunch& L, int n, int sm_count, cudaStream_t s);   // CTA-pair variant (lstm_seq2.cu)
+// ablate: timing experiments only (dsb_plan_options): 1 no cell-state traffic, 2 no h store
+void launch_lstm_seq2(const LstmSeqLaunch& L, int n, int sm_count, int ablate, cudaStream_t s);   // CTA-pair kernel (lstm_seq2.cu)
 
 }  // namespace dsb

@@ -302,7 +302,7 @@ lstm_seq2_kernel(const __grid_constant__ LstmSeqMaps maps, const LstmSeqParams p
 
 }  // namespace
 
-void launch_lstm_seq2(const LstmSeqLaunch& L, int n, int sm_count, cudaStream_t s) {
+void launch_lstm_seq2(const LstmSeqLaunch& L, int n, int sm_count, int ablate, cudaStream_t s) {
   if (n <= 0) return;
   const int m_tiles = (n + 127) / 128;
   const int m_pairs = (m_tiles + 1) / 2;
@@ -312,7 +312,6 @@ void launch_lstm_seq2(const LstmSeqLaunch& L, int n, int sm_count, cudaStream_t 
   if (clusters < 1) clusters = 1;
   LstmSeqParams p = L.p;
   p.n = n;
-  static const int ablate = getenv("DSB_ABLATE_S") ? atoi(getenv("DSB_ABLATE_S")) : 0;   // timing experiments only
   static bool configured[64][2] = {{false}};
   int dev = 0;
   DSB_CUDA(cudaGetDevice(&dev));
@@ -335,7 +334,6 @@ void launch_lstm_seq2(const LstmSeqLaunch& L, int n, int sm_count, cudaStream_t 
     int nc = 0;
     DSB_CUDA(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
     max_clusters[dev & 63] = nc > 0 ? nc : 1;
-    if (getenv("DSB_VERBOSE")) fprintf(stderr, "[lstm_seq2] max co-resident 2-CTA clusters: %d (SMs %d)\n", nc, sm_count);
   }
   if (clusters > max_clusters[dev & 63]) clusters = max_clusters[dev & 63];
   launch_pdl(kern, 2 * clusters, P_THREADS, P_SMEM, s, L.maps, p, ablate);

@@ -11,7 +11,7 @@
 
 namespace dsb {
 
-constexpr int MAX_SEG = 5;
+constexpr int MAX_SEG = 10;         // 5 taps x (hi, lo) parts in the split-operand mode
 
 enum EpiKind { EPI_CONV = 0, EPI_LSTM = 1 };
 
@@ -26,6 +26,9 @@ struct EpiParams {
   uint32_t relu_mask = 0; // bit j: ReLU on columns [16j, 16j+16)
   const void* res = nullptr; int res_ld = 0; int res_c0 = 0;   // residual added before ReLU (d0 columns)
   int Lp = 0, L = 0;      // padded row layout: rows with (row % Lp) >= L are written as zero
+  // split-operand mode (DSB_PREC_FP16X2): every activation is stored as hi = fp16(v) and lo = fp16(v - hi) in two
+  // matrices of the same shape; lo_off* = element offset from the hi matrix to its lo twin (0 = single 16-bit output)
+  long long lo_off0 = 0, lo_off1 = 0, res_lo_off = 0;
   // EPI_LSTM: columns are 4*u+g; c [M][256] fp32 updated in place, h_out [M][256]
   float* c = nullptr;
   void* h_out = nullptr;

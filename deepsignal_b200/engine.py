@@ -30,7 +30,7 @@ def _np(a, dtype, shape=None):
 class Engine(object):
     def __init__(self, device: int = 0):
         self.lib = _lib.load()
-        if self.lib.dsb_abi_version() != 1:
+        if self.lib.dsb_abi_version() != _lib.ABI_VERSION:
             raise ImportError("libdsb200 ABI version mismatch")
         h = C.c_void_p()
         rc = self.lib.dsb_create(int(device), C.byref(h))
@@ -80,10 +80,27 @@ class Engine(object):
     def set_max_chunk(self, n: int):
         self._check(self.lib.dsb_set_max_chunk(self.h, int(n)))
 
-    def workspace_bytes(self, n: int, precision="bf16") -> int:
-        return int(self.lib.dsb_workspace_bytes(self.h, int(n), _lib.PRECISIONS[precision]))
+    def set_plan_options(self, **kw):
+        """Change how the forward plan is built (``dsb_plan_options``): fused_blocks / fused_front / lstm_seq select
+        the fused kernels (default) or the one-launch-per-op references; ablate_* are timing experiments."""
+        o = _lib.PlanOptions()
+        self._check(self.lib.dsb_get_plan_options(self.h, C.byref(o)))
+        for k, v in kw.items():
+            if not hasattr(o, k):
+                raise KeyError(k)
+            setattr(o, k, int(v))
+        self._check(self.lib.dsb_set_plan_options(self.h, C.byref(o)))
 
-    def forward(self, kmer, means, stds, lens, signals, precision="bf16"):
+    def nonfinite_count(self) -> int:
+        """Samples with non-finite logits since the last call (after a device-pointer forward; sync the stream first)."""
+        n = C.c_int64(0)
+        self._check(self.lib.dsb_nonfinite_count(self.h, C.byref(n)))
+        return int(n.value)
+
+    def workspace_bytes(self, n: int, precision=_lib.DEFAULT_PRECISION) -> int:
+        return int(self.lib.dsb_workspace_bytes(self.h, int(n), _lib.PRECISIONS.get(precision, precision)))
+
+    def forward(self, kmer, means, stds, lens, signals, precision=_lib.DEFAULT_PRECISION):
         """Host arrays in, host arrays out (``dsb_forward_host``): probs f32[n,2], pred int32[n]."""
         signals = _np(signals, np.float32)
         n = signals.shape[0]
@@ -95,21 +112,21 @@ class Engine(object):
         lens = _np(lens, np.float32, (n, K)) if lens is not None else None
         probs = np.empty((n, 2), np.float32)
         pred = np.empty((n,), np.int32)
-        self._check(self.lib.dsb_forward_host(self.h, _lib.PRECISIONS[precision], n, _ptr(kmer), _ptr(means),
+        self._check(self.lib.dsb_forward_host(self.h, _lib.PRECISIONS.get(precision, precision), n, _ptr(kmer), _ptr(means),
                                               _ptr(stds), _ptr(lens), _ptr(signals), _ptr(probs), _ptr(pred)))
         return probs, pred
 
-    def forward_ptrs(self, n, kmer, means, stds, lens, signals, probs, pred, precision="bf16", host=False, stream=0):
+    def forward_ptrs(self, n, kmer, means, stds, lens, signals, probs, pred, precision=_lib.DEFAULT_PRECISION, host=False, stream=0):
         """Raw-pointer call (ints): device pointers + stream -> dsb_forward_dev, host pointers -> dsb_forward_host."""
         vp = lambda x: C.c_void_p(int(x)) if x else None
         if host:
-            self._check(self.lib.dsb_forward_host(self.h, _lib.PRECISIONS[precision], int(n), vp(kmer), vp(means),
+            self._check(self.lib.dsb_forward_host(self.h, _lib.PRECISIONS.get(precision, precision), int(n), vp(kmer), vp(means),
                                                   vp(stds), vp(lens), vp(signals), vp(probs), vp(pred)))
         else:
-            self._check(self.lib.dsb_forward_dev(self.h, _lib.PRECISIONS[precision], int(n), vp(kmer), vp(means),
+            self._check(self.lib.dsb_forward_dev(self.h, _lib.PRECISIONS.get(precision, precision), int(n), vp(kmer), vp(means),
                                                  vp(stds), vp(lens), vp(signals), vp(probs), vp(pred), vp(stream)))
 
-    def forward_torch(self, kmer, means, stds, lens, signals, precision="bf16", probs=None, pred=None):
+    def forward_torch(self, kmer, means, stds, lens, signals, precision=_lib.DEFAULT_PRECISION, probs=None, pred=None):
         """Device-resident torch tensors in / out (``dsb_forward_dev`` on torch's current stream)."""
         import torch
         n = signals.shape[0]
@@ -201,7 +218,7 @@ class Engine(object):
         return res
 
     def extract_call_torch(self, dev_reads: dict, n_reads: int, motif_seqs=("CG",), mod_loc=0,
-                           normalize_method="mad", precision="bf16", capacity=None, site_bufs=None):
+                           normalize_method="mad", precision=_lib.DEFAULT_PRECISION, capacity=None, site_bufs=None):
         """Fused extraction -> forward on device-resident reads (torch tensors keyed like ``dsb_reads``)."""
         import torch
         rd = _lib.Reads()
@@ -223,7 +240,7 @@ class Engine(object):
             setattr(st, f, site_bufs[f].data_ptr() if f in site_bufs else None)
         n_sites = C.c_int64(0)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        self._check(self.lib.dsb_extract_call_dev(self.h, _lib.PRECISIONS[precision], C.byref(rd), C.byref(prm),
+        self._check(self.lib.dsb_extract_call_dev(self.h, _lib.PRECISIONS.get(precision, precision), C.byref(rd), C.byref(prm),
                                                   C.byref(st), C.byref(n_sites), C.c_void_p(site_bufs["probs"].data_ptr()),
                                                   C.c_void_p(site_bufs["pred"].data_ptr()), C.c_void_p(stream)))
         return int(n_sites.value), site_bufs

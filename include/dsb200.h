@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DSB_ABI_VERSION 1
+#define DSB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DSB_API __attribute__((visibility("default")))
@@ -50,7 +50,9 @@ typedef enum dsb_status {
   DSB_ERR_STATE = -4,     /* e.g. forward before load_weights              */
   DSB_ERR_CAPACITY = -5,  /* caller-provided output capacity too small     */
   DSB_ERR_ARCH = -6,      /* tensor-core path needs an sm_100 device       */
-  DSB_ERR_NOMEM = -7
+  DSB_ERR_NOMEM = -7,
+  DSB_ERR_NONFINITE = -8  /* a 16-bit activation overflowed: some logits are inf/NaN (outputs are written;
+                             rerun those samples with DSB_PREC_FP32)          */
 } dsb_status;
 
 /* model-variant and precision flags of dsb_load_weights (reference flags --is_cnn/--is_rnn/
@@ -63,8 +65,13 @@ typedef enum dsb_status {
 typedef enum dsb_precision {
   DSB_PREC_FP32 = 0,      /* CUDA-core fp32 path, 1e-4 abs parity target   */
   DSB_PREC_BF16 = 1,      /* tcgen05 kind::f16 path, bf16 operands, fp32 accumulate */
-  DSB_PREC_FP16 = 2       /* same kernels and rate with fp16 operands (10-bit mantissa: 8x smaller
+  DSB_PREC_FP16 = 2,      /* same kernels and rate with fp16 operands (10-bit mantissa: 8x smaller
                              rounding error than bf16; activations must stay below 65504)       */
+  DSB_PREC_FP16X2 = 3     /* split-operand tensor-core path: every CNN activation is carried as hi + lo fp16
+                             parts (22 mantissa bits), each conv is [xh | xl] . [W ; W] on tcgen05 with fp16
+                             weights and fp32 accumulation.  This is the 16-bit mode that meets the 2e-3 /
+                             99.9 % tolerance on spread-logit checkpoints; the LSTM runs
+                             as in DSB_PREC_FP16.                                                    */
 } dsb_precision;
 
 /* One checkpoint tensor, host float32, keyed by its TF-1.x variable name (the names a
@@ -92,6 +99,18 @@ DSB_API int dsb_load_weights(dsb_ctx* ctx, const dsb_tensor* tensors, int32_t n_
  * paths).  Default 37888 = 148 SMs x 256 samples, the size at which the persistent LSTM kernel is perfectly balanced;
  * smaller values (multiples of 128) trade throughput for memory. */
 DSB_API int dsb_set_max_chunk(dsb_ctx* ctx, int64_t max_chunk);
+
+/* How the forward plan is built.  Defaults (all fused) are the product path; the un-fused variants are the
+ * references the fused kernels are tested against, and the ablate_* fields make a kernel skip part of its work for
+ * timing experiments (wrong results by design).  Takes effect for plans built after the call (plans are rebuilt). */
+typedef struct dsb_plan_options {
+  int32_t fused_blocks;   /* 1: inception kernels A + B per block; 0: one GEMM launch per conv + pool kernels   */
+  int32_t fused_front;    /* 1: conv1 + pool + conv2 + conv3 in one kernel (single 16-bit modes); 0: stem + 2 GEMMs */
+  int32_t lstm_seq;       /* 1: whole BiLSTM in one persistent kernel; 0: one GEMM launch per (dir, layer, step) */
+  int32_t ablate_a, ablate_b, ablate_gemm, ablate_lstm;
+} dsb_plan_options;
+DSB_API int dsb_get_plan_options(const dsb_ctx* ctx, dsb_plan_options* out);
+DSB_API int dsb_set_plan_options(dsb_ctx* ctx, const dsb_plan_options* opts);
 DSB_API size_t dsb_workspace_bytes(const dsb_ctx* ctx, int64_t n, int32_t precision);
 
 /* Forward of n samples (the feed_dict / fetches of call_modifications.py:168-178):
@@ -109,6 +128,10 @@ DSB_API int dsb_forward_dev(dsb_ctx* ctx, int32_t precision, int64_t n,
 DSB_API int dsb_forward_host(dsb_ctx* ctx, int32_t precision, int64_t n,
                      const int32_t* kmer, const float* means, const float* stds, const float* lens,
                      const float* signals, float* probs, int32_t* pred);
+/* Samples whose logits were not finite since the last call of this function (the counter is reset).  dsb_forward_host
+ * checks it itself and returns DSB_ERR_NONFINITE; after dsb_forward_dev / dsb_extract_call_dev call this once the
+ * stream has been synchronised. */
+DSB_API int dsb_nonfinite_count(dsb_ctx* ctx, int64_t* count);
 
 /* Per-kernel-class timing of the most recent profiled forward (CUDA events on the launch
  * stream around every launch of the class).  classes: 0 tensor-core GEMM kernels other than 1 and 3,

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.dsb_abi_version() == 1
+    assert lib.dsb_abi_version() == _lib.ABI_VERSION
 
 
 def test_no_cpu_fallback_without_device():

@@ -94,7 +94,7 @@ def test_cli_flags_and_defaults(monkeypatch):
     cli.main()
     c = seen["call"]
     assert (c.kmer_len, c.cent_signals_len, c.batch_size, c.learning_rate, c.class_num, c.is_gpu) == (17, 360, 512, 0.001, 2, "no")
-    assert (c.is_cnn, c.is_rnn, c.is_base, c.f5_batch_num, c.precision) == ("yes", "yes", "yes", 50, "fp16")
+    assert (c.is_cnn, c.is_rnn, c.is_base, c.f5_batch_num, c.precision) == ("yes", "yes", "yes", 50, "fp16x2")
 
 
 def test_shard_ranges_cover_without_overlap():
