@@ -1,25 +1,36 @@
 #!/usr/bin/env python
 """bench.py — CpG samples/sec of the call_mods hot path on N B200s (BASELINE.json metric).
 
-Workload (config.workload): BASELINE.json configs[2] — the call_mods forward on synthetic
+Headline workload (config.workload): BASELINE.json configs[2] — the call_mods forward on synthetic
 bn17/sn360 samples with the seed-17 random-init ("stress") checkpoint.  A step is one pass of
 `--samples-per-step` samples per GPU through `dsb_forward_dev` (inputs resident in HBM, 1.8 GB per
 2^20 samples — far larger than the 126 MB L2, so no L2 flush is needed between steps).  `e2e` is the
 same metric through `dsb_forward_host` with pinned HOST buffers: host->device copies of the five
 input arrays and the device->host read of probs/pred are inside the timed region.
 
-Reads shard across GPUs with no collective (one process per GPU; torch.distributed is used only
-for the barrier and the max-over-ranks of the device time) -> "scaling": "weak".
+The timed dtype defaults to "fp16x2" (split hi+lo fp16 activations on tcgen05): the 16-bit mode that
+meets BASELINE's 2e-3 / 99.9 % tolerance on this checkpoint.  The `parity` block of the JSON line is
+computed in the same run on 100,000 cfg-3 samples for the timed dtype (and, for information, for the
+faster single-rounding modes).
 
-`--impl reference` times the CPU restatement of the reference's un-folded TF graph (oracle/model_oracle.py,
-torch CPU fp32, all host threads, batch 512 like call_modifications.py:157) — TensorFlow itself
-cannot be installed in this image, so kind = "port".
+Sub-records on the same line: `extract` = configs[1] (4k synthetic reads through the extraction
+kernels: sites/s, achieved GB/s against SURVEY 8d's 2*N_raw + 9*n_bases + 1677*n_sites, per-kernel ms)
+and `e2e_reads` = configs[3] (extraction + forward, reads sharded over the ranks).
+
+Reads / samples shard across GPUs with no collective (one process per GPU; torch.distributed is used
+only for the barrier and the max-over-ranks of the device time) -> "scaling": "weak".
+
+`--impl reference` runs the reference's own `call_mods(..., is_gpu=False)` host code (oracle/_ref, unmodified:
+reader / caller / writer processes, text parsing, probability formatting) on a feature file of the same
+workload, with `sess.run` served by the torch-CPU fp32 restatement of the un-folded graph because
+TensorFlow 1.x cannot be installed in this image -> kind "port" ("TF-equivalent CPU restatement").
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -28,10 +39,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALG_BYTES_INCEPT_A = 90 * (512 + 480) + 2 * 90 * 960 + 5 * 45 * 960 + 3 * 23 * 960   # 544,320 B per sample, see roofline below
-FLOP_PER_SAMPLE = 198.61e6          # executed MACs*2 after the exact folds (SURVEY §8a/§8d)
+FLOP_PER_SAMPLE = 198.61e6          # executed MACs*2 after the exact folds (SURVEY 8a / 8d)
 BYTES_IN_PER_SAMPLE = 17 * 4 * 4 + 360 * 4   # 1712
 BYTES_OUT_PER_SAMPLE = 12
+ALG_BYTES_PER_SAMPLE = BYTES_IN_PER_SAMPLE + BYTES_OUT_PER_SAMPLE   # 1724: SURVEY 8d's algorithmic HBM bytes of the forward
+# inception kernel A (the dominant kernel): algorithmic FLOPs = 2 * cin * 240 per real row, rows = 3x90 + 5x45 + 3x23
+FLOP_INCEPT_A_PER_SAMPLE = 2.0 * 240.0 * (256 * 90 + 240 * (2 * 90 + 5 * 45 + 3 * 23))
+# activation bytes kernel A moves per sample in the single 16-bit modes (x in + 240 channels out); doubled in fp16x2
+ACT_BYTES_INCEPT_A = 90 * (512 + 480) + 2 * 90 * 960 + 5 * 45 * 960 + 3 * 23 * 960   # 544,320
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r2_traffic.json")
 
 
 def peaks():
@@ -74,43 +90,98 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    power_w=float(np.median(pw)) if pw else None, reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_baseline(n_samples, ckpt, threads=None):
-    """TF-equivalent CPU restatement (un-folded graph, fp32, batch 512) timed on the host cores."""
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the reference's own call_mods host code (oracle/ref_host.py)
+# ------------------------------------------------------------------------------------------------------------------
+def reference_call_mods(n_lines, tmp, layouts=None):
+    """Write an n_lines feature file (cfg-1 layout) + the checkpoint, run the reference's call_mods on it with the
+    requested process layouts; returns {layout: samples/s}, cores."""
+    from deepsignal_b200 import weights as W
+    from deepsignal_b200.synth import synth_features, write_feature_tsv, SEED_CFG1
+    from oracle import ref_host
+    ck = os.path.join(tmp, "stress_ckpt.npz")
+    if not os.path.exists(ck):
+        W.save_npz(ck, W.random_checkpoint(17, "stress"))
+    tsv = os.path.join(tmp, "features_%d.tsv" % n_lines)
+    if not os.path.exists(tsv):
+        write_feature_tsv(tsv, synth_features(n_lines, seed=SEED_CFG1))
+    cores = os.cpu_count() or 1
+    return ref_host.time_layouts(tsv, n_lines, ck, tmp, cores=cores, probe_only=layouts), cores
+
+
+def model_only_rate(n=2048):
+    """Steady-state rate of the sess.run stand-in alone (torch-CPU fp32, un-folded graph, batch 512, all threads).
+    Call AFTER the fork()-based runs: a used OpenMP pool does not survive fork()."""
     import torch
+    from deepsignal_b200 import weights as W
+    from deepsignal_b200.synth import synth_features, SEED_CFG1
     from oracle import model_oracle as mo
-    from deepsignal_b200.synth import synth_features
-    cores = threads or os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    f = synth_features(n_samples, seed=20260103)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ck = W.random_checkpoint(17, "stress")
+    f = synth_features(n, seed=SEED_CFG1)
     lens = f["lens"].astype(np.float32)
-    mo.forward(ckpt, f["kmer"][:64], f["means"][:64], f["stds"][:64], lens[:64], f["signals"][:64], dtype=torch.float32)
+    run = lambda i, j: mo.forward(ck, f["kmer"][i:j], f["means"][i:j], f["stds"][i:j], lens[i:j], f["signals"][i:j], dtype=torch.float32)
+    run(0, 512)
     t0 = time.perf_counter()
-    for i in range(0, n_samples, 512):
-        j = min(n_samples, i + 512)
-        mo.forward(ckpt, f["kmer"][i:j], f["means"][i:j], f["stds"][i:j], lens[i:j], f["signals"][i:j], dtype=torch.float32)
-    dt = time.perf_counter() - t0
-    return n_samples / dt, cores, dt
+    for i in range(0, n, 512):
+        run(i, min(n, i + 512))
+    return n / (time.perf_counter() - t0)
+
+
+def run_reference_arm(a):
+    workload = forward_workload()
+    per_step = int(max(4096, min(100000, 240000 // max(1, a.steps))))
+    with tempfile.TemporaryDirectory(prefix="dsb_ref_") as tmp:
+        probe, cores = reference_call_mods(2048, tmp)                     # warm-up: imports, page cache, and the layout probe
+        best = max(probe, key=probe.get)
+        for _ in range(max(0, a.warmup - 1)):
+            reference_call_mods(2048, tmp, layouts=[best])
+        t_tot, n_tot = 0.0, 0
+        for _ in range(a.steps):
+            r, _ = reference_call_mods(per_step, tmp, layouts=[best])
+            t_tot += per_step / r[best]
+            n_tot += per_step
+    val = n_tot / t_tot
+    model_only = model_only_rate()
+    sample = ("{} feature-file lines per step (configs[0] layout: 50 sites per read) through the reference's call_mods "
+              "(--is_gpu no), layout '{}' (probe on 2048 lines: {}); every step is a whole call_mods run, so its process "
+              "start-up, per-caller checkpoint load and 1-second queue polls are inside the time").format(
+                  per_step, best, {k: round(v, 1) for k, v in probe.items()})
+    print(json.dumps({
+        "impl": "reference", "metric": "CpG samples/sec (call_mods forward)", "value": val, "unit": "samples/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "samples_per_step": per_step},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
+                         "model_only_samples_per_s": model_only,
+                         "what": "reference host code verbatim (oracle/_ref) + torch-CPU fp32 restatement of the un-folded TF graph as sess.run"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return 0
+
+
+def forward_workload():
+    return "call_mods forward, bn17/sn360 synthetic samples (BASELINE configs[2]), seed-17 random-init checkpoint"
 
 
 def device_inputs(torch, n, dev, seed):
-    """cfg-3 distributions generated on the device (SURVEY §8d)."""
+    """cfg-3 distributions generated on the device (SURVEY 8d)."""
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     kmer = torch.randint(0, 4, (n, 17), device=dev, dtype=torch.int32, generator=g)
@@ -128,64 +199,111 @@ def device_inputs(torch, n, dev, seed):
     return kmer.contiguous(), means.contiguous(), stds.contiguous(), lens.contiguous(), signals.contiguous()
 
 
-def bench_reads(a, eng, torch, dev, rank, world, barrier, max_over_ranks, ckpt):
+def parity_block(eng, ckpt, precision, n=100000, pin_n=2048):
+    """Tolerance report of configs[2] on the checkpoint the bench times: the timed dtype against the library's fp32 path
+    on `n` cfg-3 samples, the fp32 path itself pinned to the float64 oracle on the first `pin_n` of them."""
+    from deepsignal_b200.synth import synth_features, SEED_CFG3
+    from oracle import model_oracle as mo
+    f = synth_features(n, seed=SEED_CFG3)
+    x = (f["kmer"], f["means"], f["stds"], f["lens"].astype(np.float32), f["signals"])
+    ref, rpred = eng.forward(*x, precision="fp32")
+    o64, _ = mo.forward(ckpt, *[t[:pin_n] for t in x])
+    pin = float(np.abs(ref[:pin_n] - o64).max())
+    margin = np.abs(ref[:, 0] - ref[:, 1])
+    buckets = [(0.0, 5e-4), (5e-4, 1e-3), (1e-3, 2e-3), (2e-3, 5e-3), (5e-3, 1.0)]
+
+    def stats(prec):
+        got, pred = eng.forward(*x, precision=prec)
+        d = np.abs(got - ref)
+        flips = pred != rpred
+        d64 = np.abs(got[:pin_n] - o64)
+        return {"max_abs_dp": float(d.max()), "mean_abs_dp": float(d.mean()), "identical_calls": float((~flips).mean()),
+                "flips": int(flips.sum()),
+                "flips_by_margin": {"{:g}-{:g}".format(lo, hi): int((flips & (margin >= lo) & (margin < hi)).sum()) for lo, hi in buckets},
+                "max_abs_dp_vs_f64_oracle_subset": float(d64.max())}
+
+    out = {"n": n, "checkpoint": "seed-17 'stress' (the timed one)", "dtype": precision,
+           "reference": "libdsb200 fp32 path on all n; float64 oracle (oracle/model_oracle.py) on the first %d" % pin_n,
+           "fp32_path_vs_f64_oracle_max_abs_dp": pin, "tolerance": {"max_abs_dp": 2e-3, "identical_calls": 0.999}}
+    out.update(stats(precision))
+    out["meets_tolerance"] = bool(out["max_abs_dp"] + pin <= 2e-3 and out["identical_calls"] >= 0.999)
+    out["other_modes"] = {p: stats(p) for p in ("fp16x2", "fp16", "bf16") if p != precision}
+    return out
+
+
+def read_traffic(kernel_prefix):
+    """ncu dram bytes per launch of a kernel from profiles/r2_traffic.json (written by profiles/traffic_from_ncu.py)."""
+    if not os.path.exists(TRAFFIC_JSON):
+        return None, None
+    with open(TRAFFIC_JSON) as fh:
+        tj = json.load(fh)
+    for k, v in tj.get("kernels", {}).items():
+        if k.startswith(kernel_prefix) and v.get("launches"):
+            return v["dram_bytes"] / v["launches"], tj
+    return None, tj
+
+
+def bench_reads(a, eng, torch, dev, rank, world, barrier, max_over_ranks):
     """configs[1] (extraction only) and configs[3] (extraction + forward) on synthetic resquiggled reads."""
-    from deepsignal_b200.synth import synth_reads, SEED_CFG2, SEED_CFG4
-    from oracle import features_oracle as fo
-    rb = synth_reads(a.reads, seed=(SEED_CFG2 if a.workload == "extract" else SEED_CFG4) + rank)
+    from deepsignal_b200.synth import synth_reads, SEED_CFG4
+    rb = synth_reads(a.reads, seed=SEED_CFG4 + rank)
     dr = eng.reads_to_device(rb, dev)
     n_raw, n_ev = int(rb.raw_off[-1]), int(rb.ev_off[-1])
     cap = max(1024, int(n_ev * 0.03))
     bufs = eng.alloc_site_bufs(cap, dev)
-
-    def step():
-        if a.workload == "extract":
-            return eng.extract_torch(dr, rb.n_reads, bufs)
-        return eng.extract_call_torch(dr, rb.n_reads, precision=a.precision, site_bufs=bufs)[0]
-
-    for _ in range(a.warmup):
-        n_sites = step()
-    sampler = ClockSampler(torch.cuda.current_device())
-    barrier()
-    sampler.start()
-    l0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        n_sites = step()
-    e1.record()
-    barrier()
-    launches = eng.launch_count() - l0
-    clocks = sampler.stop()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    sites_s = world * n_sites * a.steps / (ms * 1e-3)
-    alg_bytes = 2.0 * n_raw + 9.0 * n_ev + 1677.0 * n_sites          # SURVEY §8d per-read figure
     pk = peaks()
-    out = {
-        "metric": "CpG samples/sec ({})".format("extract_features" if a.workload == "extract" else "extract + call_mods"),
-        "value": sites_s, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64" if a.workload == "extract" else a.precision, "data": "synthetic",
-        "config": {"workload": "BASELINE configs[{}]: {} synthetic tombo-style R9.4 reads per GPU, {} raw samples, {} bases, {} CpG sites".format(
-            1 if a.workload == "extract" else 3, rb.n_reads, n_raw, n_ev, n_sites),
-            "reads_per_s": world * rb.n_reads * a.steps / (ms * 1e-3),
-            "l2": "raw signal {} MB + outputs {} MB per step exceed the 126 MB L2".format(2 * n_raw >> 20, int(1677 * n_sites) >> 20)},
-        "clocks": clocks, "gpu_launches": int(launches)}
-    if a.workload == "extract":
-        ach = alg_bytes * a.steps / (ms * 1e-3) / 1e9
-        out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                           "traffic": None, "kernel": "extraction kernel chain (5 launches per batch)",
-                           "peak_source": pk["source"]}
-        if rank == 0 and not a.no_cpu_baseline:
-            k = min(rb.n_reads, 1500)          # ~10 s of single-core NumPy work
-            t0 = time.perf_counter()
-            ns = 0
-            for i in range(k):
-                ns += len(fo.extract_read(rb.read_dict(i), ["CG"]))
-            dt = time.perf_counter() - t0
-            out["cpu_baseline"] = {"value": ns / dt, "unit": "samples/s", "cores": 1, "kind": "port",
-                                   "sample": "{} reads ({} sites) through the NumPy restatement of _extract_features, {:.1f} s".format(k, ns, dt)}
-    return out
+    steps = max(1, min(a.steps, 3))
+    reps = max(1, a.e2e_reads // a.reads)          # the device-resident read batch is processed `reps` times per e2e step
+    res = {}
+
+    def timed(fn, n_steps):
+        fn()
+        barrier()
+        l0 = eng.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            n_sites = fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), n_sites, eng.launch_count() - l0
+
+    # ---- configs[1]: extraction only
+    ms, n_sites, launches = timed(lambda: eng.extract_torch(dr, rb.n_reads, bufs), steps * 4)
+    ms /= steps * 4
+    alg_bytes = 2.0 * n_raw + 9.0 * n_ev + 1677.0 * n_sites          # SURVEY 8d per-read figure
+    eng.set_profiling(True)
+    eng.extract_torch(dr, rb.n_reads, bufs)
+    torch.cuda.synchronize(dev)
+    prof = {k: round(v["ms"], 4) for k, v in eng.profile().items() if k.startswith("x_")}
+    eng.set_profiling(False)
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    res["extract"] = {
+        "workload": "BASELINE configs[1]: {} synthetic tombo-style R9.4 reads per GPU ({} raw samples, {} bases, {} CpG sites), "
+                    "MAD normalisation + per-base mean/std/len + 360-point window + k-mer codes".format(rb.n_reads, n_raw, n_ev, n_sites),
+        "sites_per_s": world * n_sites / (ms * 1e-3), "reads_per_s": world * rb.n_reads / (ms * 1e-3), "ms_per_step": ms,
+        "dtype": "f64", "gpu_launches_per_step": launches // (steps * 4),
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                     "algorithmic_bytes": alg_bytes, "formula": "2*N_raw + 9*n_bases + 1677*n_sites (SURVEY 8d)",
+                     "traffic": read_traffic("x_chain")[0], "kernel": "extraction kernel chain"},
+        "per_kernel_ms": prof}
+    # ---- configs[3]: extraction + forward, reads sharded by rank
+    def e2e_step():
+        n = 0
+        for _ in range(reps):
+            n = eng.extract_call_torch(dr, rb.n_reads, precision=a.precision, site_bufs=bufs)[0]
+        return n
+    ms, n_sites, launches = timed(e2e_step, steps)
+    ms /= steps
+    res["e2e_reads"] = {
+        "workload": "BASELINE configs[3]: extract_features + call_mods on {} reads per GPU per step (a device-resident batch of {} "
+                    "synthetic reads processed {} times; ~{} CpG sites per GPU per step), reads sharded over {} rank(s), no collective".format(
+                        reps * rb.n_reads, rb.n_reads, reps, reps * n_sites, world),
+        "reads_total_per_step": world * reps * rb.n_reads,
+        "reads_per_s": world * reps * rb.n_reads / (ms * 1e-3), "sites_per_s": world * reps * n_sites / (ms * 1e-3),
+        "ms_per_step": ms, "dtype": a.precision, "gpu_launches_per_step": launches // steps,
+        "whole_step_frac_of_tensor_peak": reps * n_sites / (ms * 1e-3) * FLOP_PER_SAMPLE / 1e12 / pk["bf16_tflops_sustained"]}
+    return res
 
 
 def main():
@@ -193,17 +311,20 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-probe"],
+                    help="cpu-probe: internal (the cpu_baseline leg runs in a fresh process so that the reference's fork()ed "
+                         "workers never inherit a CUDA context or a used OpenMP pool)")
+    ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "bf16", "fp16", "fp32"])
     ap.add_argument("--samples-per-step", type=int, default=1 << 20)
     ap.add_argument("--e2e-samples", type=int, default=1 << 19)
     ap.add_argument("--max-chunk", type=int, default=37888)
-    ap.add_argument("--cpu-samples", type=int, default=16384)
+    ap.add_argument("--cpu-samples", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="forward", choices=["forward", "extract", "e2e"],
-                    help="forward = BASELINE configs[2] (default, the metric's workload); extract = configs[1] "
-                         "(4k reads, extraction only); e2e = configs[3] (extract + call_mods, read-sharded)")
-    ap.add_argument("--reads", type=int, default=4000)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-reads", action="store_true", help="skip the extract / e2e_reads sub-records")
+    ap.add_argument("--parity-samples", type=int, default=100000)
+    ap.add_argument("--reads", type=int, default=4000, help="synthetic reads per device-resident batch (configs[1])")
+    ap.add_argument("--e2e-reads", type=int, default=128000, help="reads per GPU per e2e_reads step (configs[3]: 1 M reads at 8 GPUs)")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
@@ -212,37 +333,24 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    from deepsignal_b200 import weights as W
-    ckpt = W.random_checkpoint(17, "stress")
-    workload = "call_mods forward, bn17/sn360 synthetic samples (BASELINE configs[2]), seed-17 random-init checkpoint"
-
     if a.impl == "reference":
         if rank != 0:
             return 0
-        per_step = max(512, a.cpu_samples // 4)
-        for _ in range(max(1, min(a.warmup, 1))):
-            cpu_baseline(512, ckpt)
-        t_tot, n_tot = 0.0, 0
-        cores = os.cpu_count() or 1
-        for _ in range(a.steps):
-            v, cores, dt = cpu_baseline(per_step, ckpt)
-            t_tot += dt
-            n_tot += per_step
-        val = n_tot / t_tot
-        sample = "{} samples per step, torch-CPU fp32 restatement of the un-folded graph, batch 512".format(per_step)
-        print(json.dumps({
-            "impl": "reference", "metric": "CpG samples/sec (call_mods forward)", "value": val, "unit": "samples/s",
-            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / a.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "samples_per_step": per_step},
-            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return run_reference_arm(a)
+    if a.impl == "cpu-probe":
+        with tempfile.TemporaryDirectory(prefix="dsb_cpu_") as tmp:
+            t0 = time.perf_counter()
+            res, cores = reference_call_mods(a.cpu_samples, tmp)
+            dt = time.perf_counter() - t0
+            print(json.dumps({"layouts": res, "cores": cores, "seconds": dt, "model_only": model_only_rate()}))
         return 0
 
     import torch
     import torch.distributed as dist
+    from deepsignal_b200 import weights as W
     from deepsignal_b200.engine import Engine
 
+    ckpt = W.random_checkpoint(17, "stress")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -263,14 +371,6 @@ def main():
     eng = Engine(local_rank)
     eng.load_weights(ckpt)
     eng.set_max_chunk(a.max_chunk)
-    if a.workload != "forward":
-        out = bench_reads(a, eng, torch, dev, rank, world, barrier, max_over_ranks, ckpt)
-        if rank == 0:
-            print(json.dumps(out))
-        eng.close()
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
     n = a.samples_per_step
     x = device_inputs(torch, n, dev, 20260103 + rank)
     probs = torch.empty((n, 2), dtype=torch.float32, device=dev)
@@ -296,6 +396,7 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * n * a.steps / (ms * 1e-3)
     frac_called = float(pred.float().mean().item())
+    nonfinite = eng.nonfinite_count()
 
     # ---- per-kernel roofline: one extra profiled pass (CUDA events around every launch, single stream)
     pk = peaks()
@@ -304,39 +405,38 @@ def main():
     torch.cuda.synchronize(dev)
     prof = eng.profile()
     eng.set_profiling(False)
-    tc = [prof[k] for k in ("gemm", "lstm_gemm", "incept_a")]
-    tc_ms = sum(v["ms"] for v in tc)
-    tc_flops = sum(v["flops"] for v in tc)
-    tc_launches = sum(v["launches"] for v in tc)
-    traffic_a, traffic_tc = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")      # ncu dram__bytes_{read,write}.sum of the same command, per launch
-    if os.path.exists(tp):
-        with open(tp) as fh:
-            tj = json.load(fh)
-        ka = [v for k, v in tj.get("kernels", {}).items() if k.startswith("incept_a_kernel")]
-        if ka:
-            traffic_a = ka[0]["dram_MB"] * 1e6 / ka[0]["launches"] * (n / tj["chunk_samples"] if n < tj["chunk_samples"] else 1.0)
-        traffic_tc = tj.get("tensor_core_dram_bytes_per_launch")
-    # dominant kernel = incept_a_kernel (11 launches per chunk, ~35 % of the step): HBM-bound.  Algorithmic bytes per sample
-    # (DESIGN.md section 4): sum over the 11 blocks of L_b real rows x (2*cin_b in + 480 out) = 544,320 B.
+    fwd = {k: v for k, v in prof.items() if not k.startswith("x_") and v["launches"]}
+    step_ms = sum(v["ms"] for v in fwd.values())
     a_prof = prof["incept_a"]
-    a_bytes = ALG_BYTES_INCEPT_A * n
-    a_ach = a_bytes / (a_prof["ms"] * 1e-3) / 1e9 if a_prof["ms"] > 0 else 0.0
-    chunks = -(-n // a.max_chunk)
-    roofline = {"bound": "hbm", "achieved": a_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a_ach / pk["hbm_gbs"],
-                "traffic": traffic_a, "traffic_source": "profiles/r1_traffic.json (ncu dram bytes per incept_a_kernel launch, one 37888-sample chunk; algorithmic: %.0f)" % (a_bytes / max(a_prof["launches"], 1)),
-                "kernel": "incept_a_kernel (inception block, first half: 1x1 convs + in-SM max pool; 11 launches per chunk)",
-                "launches_profiled": a_prof["launches"], "avg_launch_ms": a_prof["ms"] / max(a_prof["launches"], 1),
-                "share_of_step": a_prof["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
-                "peak_source": pk["source"] + ", STREAM-style copy",
-                "breakdown_ms": {k: v["ms"] for k, v in prof.items()},
-                # all tensor-core kernels together (front end, inception A/B, LSTM) against the tensor roofline
-                "tensor": {"achieved": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                           "frac": (tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0) / pk["bf16_tflops_sustained"],
-                           "launches_profiled": tc_launches, "traffic": traffic_tc,
-                           "peak_source": "sustained bf16 figure (kernels timed inside a long step)"},
-                "whole_step_frac_of_tensor_peak": value / world * FLOP_PER_SAMPLE / 1e12 / pk["bf16_tflops_sustained"],
-                "chunks_per_step": chunks}
+    a_ms = max(a_prof["ms"], 1e-9)
+    a_tflops = FLOP_INCEPT_A_PER_SAMPLE * n / (a_ms * 1e-3) / 1e12
+    traffic_a, tj = read_traffic("incept_a_kernel")
+    parts = 2 if a.precision == "fp16x2" else 1
+    tc_ms = sum(v["ms"] for k, v in fwd.items() if k != "elementwise")
+    roofline = {
+        # the forward is tensor-bound; `achieved` = ALGORITHMIC FLOPs of the dominant kernel (2*cin*240 per real row,
+        # the un-split count) / its measured launch time; in fp16x2 the kernel executes twice that many tensor FLOPs.
+        "bound": "tensor", "achieved": a_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": a_tflops / pk["bf16_tflops_sustained"], "traffic": traffic_a,
+        "kernel": "incept_a_kernel (inception block, first half: the 240-channel 1x1 convs + in-SM 1x3 max pool; 11 launches per chunk)",
+        "algorithmic_flops_per_launch": FLOP_INCEPT_A_PER_SAMPLE * n / max(a_prof["launches"], 1),
+        "executed_over_algorithmic_flops": parts,
+        "launches_profiled": a_prof["launches"], "avg_launch_ms": a_ms / max(a_prof["launches"], 1),
+        "share_of_step": a_ms / max(step_ms, 1e-9),
+        "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+        "breakdown_ms": {k: round(v["ms"], 3) for k, v in fwd.items()},
+        # why the tensor fraction is what it is: the kernel streams activations at HBM speed
+        "hbm": {"achieved": parts * ACT_BYTES_INCEPT_A * n / (a_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": parts * ACT_BYTES_INCEPT_A * n / (a_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                "activation_bytes": parts * ACT_BYTES_INCEPT_A * n, "algorithmic_bytes": ALG_BYTES_PER_SAMPLE * n,
+                "traffic": (traffic_a * a_prof["launches"]) if traffic_a else None,
+                "note": "activation_bytes = what the layer-per-kernel design moves through HBM for this kernel (x in + 240 channels out, "
+                        "hi+lo in fp16x2); algorithmic_bytes = SURVEY 8d's 1724 B/sample (inputs + outputs of the whole forward)"},
+        "all_tensor_kernels": {"achieved": sum(v["flops"] for k, v in fwd.items() if k != "elementwise") / (max(tc_ms, 1e-9) * 1e-3) / 1e12,
+                               "unit": "TFLOP/s", "peak": pk["bf16_tflops_sustained"]},
+        "whole_step_frac_of_tensor_peak": value / world * FLOP_PER_SAMPLE / 1e12 / pk["bf16_tflops_sustained"],
+        "chunks_per_step": -(-n // a.max_chunk)}
+    roofline["all_tensor_kernels"]["frac"] = roofline["all_tensor_kernels"]["achieved"] / pk["bf16_tflops_sustained"]
 
     # ---- end to end through the host entry point (pinned host buffers, copies inside the timed region)
     ne = a.e2e_samples
@@ -363,19 +463,37 @@ def main():
         "metric": "CpG samples/sec (call_mods forward)", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
-        "config": {"workload": workload, "samples_per_step_per_gpu": n, "max_chunk": a.max_chunk,
+        "config": {"workload": forward_workload(), "samples_per_step_per_gpu": n, "max_chunk": a.max_chunk,
                    "l2": "inputs (1.8 GB per 2^20 samples) and per-chunk activations exceed the 126 MB L2; no flush needed",
                    "parallelism": "reads sharded, {} replica(s), no collective".format(world),
-                   "frac_called_modified": frac_called, "e2e_matches_device_path": same},
+                   "frac_called_modified": frac_called, "e2e_matches_device_path": same, "nonfinite_samples": nonfinite},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": ne * BYTES_IN_PER_SAMPLE,
                 "d2h_bytes_per_step": ne * BYTES_OUT_PER_SAMPLE, "samples_per_step_per_gpu": ne},
         "roofline": roofline,
     }
+    del hx, x, probs, pred
+    torch.cuda.empty_cache()
+    if not a.no_reads:
+        out.update(bench_reads(a, eng, torch, dev, rank, world, barrier, max_over_ranks))
+    if rank == 0 and not a.no_parity:
+        out["parity"] = parity_block(eng, ckpt, a.precision, n=a.parity_samples)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v, cores, dt = cpu_baseline(a.cpu_samples, ckpt)
-        out["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                               "sample": "{} samples, torch-CPU fp32 restatement of the un-folded reference graph, batch 512, {:.1f} s".format(a.cpu_samples, dt)}
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+        pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-probe", "--cpu-samples", str(a.cpu_samples)],
+                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env, timeout=1800)
+        pj = json.loads(pr.stdout.strip().splitlines()[-1])
+        res, cores, dt = pj["layouts"], pj["cores"], pj["seconds"]
+        best = max(res, key=res.get)
+        out["cpu_baseline"] = {
+            "value": res[best], "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "{} feature-file lines (configs[0] layout) through the reference's call_mods host code (oracle/_ref, verbatim) with the "
+                      "torch-CPU fp32 restatement of the un-folded graph as sess.run; both process layouts timed ({:.0f} s in all), "
+                      "best = '{}'".format(a.cpu_samples, dt, best),
+            "layouts": {k: round(v, 1) for k, v in res.items()},
+            "model_only_samples_per_s": pj.get("model_only")}
+    if world > 1:
+        barrier()
     if rank == 0:
         print(json.dumps(out))
     eng.close()

@@ -235,7 +235,12 @@ int dsb_extract_dev(dsb_ctx* ctx, const dsb_reads* reads, const dsb_extract_para
                     int64_t* n_sites, double* read_shift, double* read_scale, void* cuda_stream) {
   if (!ctx) return DSB_ERR_INVALID;
   return guarded(ctx, [&] {
-    dsb::extract_dev(ctx, reads, params, sites, n_sites, read_shift, read_scale, reinterpret_cast<cudaStream_t>(cuda_stream));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    struct Collect {        // also when extract_dev leaves with DSB_ERR_CAPACITY
+      dsb_ctx* c; cudaStream_t s;
+      ~Collect() { if (c->prof.enabled) { cudaStreamSynchronize(s); c->prof.collect(); } }
+    } collect{ctx, s};
+    dsb::extract_dev(ctx, reads, params, sites, n_sites, read_shift, read_scale, s);
   });
 }
 
@@ -323,6 +328,7 @@ int dsb_extract_host(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params
     if (read_shift) DSB_CUDA(cudaMemcpyAsync(read_shift, dshift.p, R * 8, cudaMemcpyDeviceToHost, s));
     if (read_scale) DSB_CUDA(cudaMemcpyAsync(read_scale, dscale.p, R * 8, cudaMemcpyDeviceToHost, s));
     DSB_CUDA(cudaStreamSynchronize(s));
+    if (ctx->prof.enabled) ctx->prof.collect();
     if (code != DSB_OK) throw dsb::Error{code, msg};
   });
 }

@@ -126,16 +126,19 @@ void fold_model(const dsb_tensor* tensors, int n, uint32_t flags, int kmer_len, 
                 FoldedModel& out);
 
 // ---- profiling ------------------------------------------------------------------------------
-enum KClass { KC_GEMM = 0, KC_LSTM = 1, KC_ELEM = 2, KC_INCEPT_A = 3, KC_COUNT = 4 };   // KC_INCEPT_A: the dominant kernel, timed separately
+// forward: KC_INCEPT_A is the dominant kernel, timed separately; KC_INCEPT_B the second inception kernel; KC_FRONT conv1..conv3.
+// extraction (extract.cu): one class per kernel of the chain.
+enum KClass { KC_GEMM = 0, KC_LSTM = 1, KC_ELEM = 2, KC_INCEPT_A = 3, KC_INCEPT_B = 4, KC_FRONT = 5,
+              KC_X_NORM = 6, KC_X_SITES = 7, KC_X_LUT = 8, KC_X_BASE = 9, KC_X_FEAT = 10, KC_COUNT = 11 };
 
 struct Profiler {
   bool enabled = false;
   struct Rec { cudaEvent_t a, b; int cls; double flops; };
   std::vector<Rec> recs;
   std::vector<cudaEvent_t> pool;
-  double ms[KC_COUNT] = {0, 0, 0, 0};
-  double flops[KC_COUNT] = {0, 0, 0, 0};
-  int64_t launches[KC_COUNT] = {0, 0, 0, 0};
+  double ms[KC_COUNT] = {};
+  double flops[KC_COUNT] = {};
+  int64_t launches[KC_COUNT] = {};
   cudaEvent_t get() {
     if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
     cudaEvent_t e;
@@ -188,6 +191,26 @@ struct dsb_ctx {
 };
 
 namespace dsb {
+struct Timer {       // optional CUDA-event bracket around one or more launches of a class (ctx->prof.enabled)
+  dsb_ctx* ctx;
+  cudaStream_t s;
+  bool on;
+  Profiler::Rec rec;
+  Timer(dsb_ctx* c, cudaStream_t st, int cls, double flops) : ctx(c), s(st), on(c->prof.enabled) {
+    if (!on) return;
+    rec.a = c->prof.get();
+    rec.b = c->prof.get();
+    rec.cls = cls;
+    rec.flops = flops;
+    cudaEventRecord(rec.a, s);
+  }
+  ~Timer() {
+    if (!on) return;
+    cudaEventRecord(rec.b, s);
+    ctx->prof.recs.push_back(rec);
+  }
+};
+
 // forward.cu
 void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, const float* means,
                  const float* stds, const float* lens, const float* signals, float* probs, int32_t* pred,

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
     float a = b;
 #pragma unroll
     for (int t = 0; t < 7; ++t) a = fmaf(w[t], win[t], a);
-    return (q >= 0 && q < p.L1) ? fmaxf(a, 0.f) : 0.f;     // ReLU; invalid cells contribute 0 (<= every valid value)
+    return (q >= 0 && q < p.L1) ? relu_keep_nan(a) : 0.f;     // ReLU; invalid cells contribute 0 (<= every valid value)
   };
   auto slide = [&]() {
     ++q;

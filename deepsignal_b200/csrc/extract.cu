@@ -337,12 +337,19 @@ __device__ __forceinline__ bool site_at(const uint8_t* bases, int nb, int i, con
   return motif_hit(bases + i, m);
 }
 
+// A read whose normalisation is undefined (no raw samples, non-positive scaling: read_norm_kernel leaves it without a
+// LUT) contributes no sites, like a read the reference fails on and drops (extract_features.py:281-283).
+__device__ __forceinline__ bool read_usable(const int64_t* raw_off, const double* scaling, int64_t r) {
+  return raw_off[r + 1] > raw_off[r] && scaling[r] > 0.0;
+}
+
 __global__ void __launch_bounds__(128) site_count_kernel(const uint8_t* ev_base, const int64_t* ev_off, int64_t R,
+                                                         const int64_t* raw_off, const double* scaling,
                                                          const MotifSet m, int64_t* counts) {
   __shared__ int sh[4];
   for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
     const uint8_t* b = ev_base + ev_off[r];
-    const int nb = (int)(ev_off[r + 1] - ev_off[r]);
+    const int nb = read_usable(raw_off, scaling, r) ? (int)(ev_off[r + 1] - ev_off[r]) : 0;
     int c = 0;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) c += site_at(b, nb, i, m) ? 1 : 0;
 #pragma unroll
@@ -385,12 +392,13 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int64_t* counts, int64
   if (threadIdx.x == 0) { offsets[R] = carry; *total = carry; }
 }
 
-__global__ void __launch_bounds__(128) site_emit_kernel(const uint8_t* ev_base, const int64_t* ev_off, int64_t R, const MotifSet m,
+__global__ void __launch_bounds__(128) site_emit_kernel(const uint8_t* ev_base, const int64_t* ev_off, int64_t R,
+                                                        const int64_t* raw_off, const double* scaling, const MotifSet m,
                                                         const int64_t* offsets, int64_t capacity, int32_t* site_read, int32_t* site_loc) {
   __shared__ int wcnt[4];
   for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
     const uint8_t* b = ev_base + ev_off[r];
-    const int nb = (int)(ev_off[r + 1] - ev_off[r]);
+    const int nb = read_usable(raw_off, scaling, r) ? (int)(ev_off[r + 1] - ev_off[r]) : 0;
     int64_t run = offsets[r];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int base = 0; base < nb; base += blockDim.x) {
@@ -549,18 +557,24 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
   w.lut_off.ensure((R + 1) * sizeof(int64_t));
   NormParams np{rd->raw, rd->raw_off, rd->scaling, rd->offset, R, prm->normalize_method,
                 w.shift.as<double>(), w.scale.as<double>(), w.scratch.as<uint32_t>(), w.vmin.as<int32_t>(), w.bins.as<int64_t>()};
-  read_norm_kernel<<<grid_norm, NORM_THREADS, 0, s>>>(np);
+  {
+    Timer tm(ctx, s, KC_X_NORM, 0);
+    read_norm_kernel<<<grid_norm, NORM_THREADS, 0, s>>>(np);
+  }
   DSB_CUDA(cudaGetLastError());
   MotifSet ms;
   memset(&ms, 0, sizeof ms);
   ms.n = prm->n_motifs; ms.len = prm->motif_len; ms.mod_loc = prm->mod_loc; ms.nbh = (prm->kmer_len - 1) / 2;
   memcpy(ms.seq, prm->motifs, (size_t)ms.n * ms.len);
   const int grid_r = (int)std::min<int64_t>(R, (int64_t)ctx->sm_count * 16);
-  site_count_kernel<<<grid_r, 128, 0, s>>>(rd->ev_base, rd->ev_off, R, ms, w.counts.as<int64_t>());
-  DSB_CUDA(cudaGetLastError());
   w.total.ensure(2 * sizeof(int64_t));
-  scan_kernel<<<1, 1024, 0, s>>>(w.counts.as<int64_t>(), w.offsets.as<int64_t>(), R, w.total.as<int64_t>());
-  scan_kernel<<<1, 1024, 0, s>>>(w.bins.as<int64_t>(), w.lut_off.as<int64_t>(), R, w.total.as<int64_t>() + 1);
+  {
+    Timer tm(ctx, s, KC_X_SITES, 0);
+    site_count_kernel<<<grid_r, 128, 0, s>>>(rd->ev_base, rd->ev_off, R, rd->raw_off, rd->scaling, ms, w.counts.as<int64_t>());
+    DSB_CUDA(cudaGetLastError());
+    scan_kernel<<<1, 1024, 0, s>>>(w.counts.as<int64_t>(), w.offsets.as<int64_t>(), R, w.total.as<int64_t>());
+    scan_kernel<<<1, 1024, 0, s>>>(w.bins.as<int64_t>(), w.lut_off.as<int64_t>(), R, w.total.as<int64_t>() + 1);
+  }
   DSB_CUDA(cudaGetLastError());
   ctx->launches += 4;
   int64_t totals[2] = {0, 0};
@@ -570,8 +584,11 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
   *n_sites = total;
   w.lut.ensure(std::max<int64_t>(total_bins, 1) * sizeof(double));
   if (total_bins > 0) {
-    lut_kernel<<<(unsigned)((total_bins + 255) / 256), 256, 0, s>>>(w.lut_off.as<int64_t>(), w.vmin.as<int32_t>(), rd->scaling, rd->offset,
-                                                                    w.shift.as<double>(), w.scale.as<double>(), R, total_bins, w.lut.as<double>());
+    {
+      Timer tm(ctx, s, KC_X_LUT, 0);
+      lut_kernel<<<(unsigned)((total_bins + 255) / 256), 256, 0, s>>>(w.lut_off.as<int64_t>(), w.vmin.as<int32_t>(), rd->scaling, rd->offset,
+                                                                      w.shift.as<double>(), w.scale.as<double>(), R, total_bins, w.lut.as<double>());
+    }
     DSB_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -588,18 +605,27 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
       if (!sr) sr = w.tmp_read.as<int32_t>();
       if (!sl) sl = w.tmp_loc.as<int32_t>();
     }
-    site_emit_kernel<<<grid_r, 128, 0, s>>>(rd->ev_base, rd->ev_off, R, ms, w.offsets.as<int64_t>(), emit, sr, sl);
+    {
+      Timer tm(ctx, s, KC_X_SITES, 0);
+      site_emit_kernel<<<grid_r, 128, 0, s>>>(rd->ev_base, rd->ev_off, R, rd->raw_off, rd->scaling, ms, w.offsets.as<int64_t>(), emit, sr, sl);
+    }
     DSB_CUDA(cudaGetLastError());
     if (total_ev > 0) {
       w.need.ensure((size_t)total_ev);
       DSB_CUDA(cudaMemsetAsync(w.need.p, 0, (size_t)total_ev, s));
       const int64_t marks = emit * prm->kmer_len;
-      mark_need_kernel<<<(unsigned)((marks + 255) / 256), 256, 0, s>>>(sr, sl, rd->ev_off, emit, prm->kmer_len, w.need.as<uint8_t>());
+      {
+        Timer tm(ctx, s, KC_X_SITES, 0);
+        mark_need_kernel<<<(unsigned)((marks + 255) / 256), 256, 0, s>>>(sr, sl, rd->ev_off, emit, prm->kmer_len, w.need.as<uint8_t>());
+      }
       DSB_CUDA(cudaGetLastError());
       BaseParams bp{rd->raw, rd->raw_off, rd->ev_start, rd->ev_len, rd->ev_off, R, total_ev,
                     w.lut.as<double>(), w.lut_off.as<int64_t>(), w.vmin.as<int32_t>(),
                     w.base_mean.as<double>(), w.base_std.as<double>(), w.base_len.as<int32_t>(), w.need.as<uint8_t>()};
-      base_stats_kernel<<<(unsigned)((total_ev + 127) / 128), 128, 0, s>>>(bp);
+      {
+        Timer tm(ctx, s, KC_X_BASE, 0);
+        base_stats_kernel<<<(unsigned)((total_ev + 127) / 128), 128, 0, s>>>(bp);
+      }
       DSB_CUDA(cudaGetLastError());
       ctx->launches += 2;
     }
@@ -611,7 +637,10 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
     sp.out = *sites;
     sp.n_sites = emit;
     sp.klen = prm->kmer_len; sp.slen = prm->signal_len;
-    site_feature_kernel<<<(unsigned)((emit + SITE_WARPS - 1) / SITE_WARPS), SITE_WARPS * 32, 0, s>>>(sp);
+    {
+      Timer tm(ctx, s, KC_X_FEAT, 0);
+      site_feature_kernel<<<(unsigned)((emit + SITE_WARPS - 1) / SITE_WARPS), SITE_WARPS * 32, 0, s>>>(sp);
+    }
     DSB_CUDA(cudaGetLastError());
     ctx->launches += 2;
   }

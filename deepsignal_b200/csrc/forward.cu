@@ -265,7 +265,7 @@ struct Builder {
           st.kind = ST_FRONT;
           st.stream = 0;
           st.rows_per_sample = Lp2;
-          st.kclass = KC_GEMM;
+          st.kclass = KC_FRONT;
           st.flops_per_row = 2.0 * (64.0 * 128.0 + 384.0 * 256.0) * (double)L2 / (double)Lp2;
           if (place) {
             const bool f16 = std::is_same<T, __half>::value;
@@ -335,7 +335,7 @@ struct Builder {
             float* biasB = reinterpret_cast<float*>(wa.take(208 * sizeof(float)));
             Step sa, sb;
             sa.kind = ST_INCEPT_A; sa.stream = 0; sa.rows_per_sample = Lp; sa.kclass = KC_INCEPT_A;
-            sb.kind = ST_INCEPT_B; sb.stream = 0; sb.rows_per_sample = Lp; sb.kclass = KC_GEMM;
+            sb.kind = ST_INCEPT_B; sb.stream = 0; sb.rows_per_sample = Lp; sb.kclass = KC_INCEPT_B;
             sa.flops_per_row = 2.0 * (double)cin * 240.0 * (double)L / (double)Lp;
             sb.flops_per_row = 2.0 * (96.0 * 48 + 160.0 * 48 + 96.0 * 64 + 64.0 * 48) * (double)L / (double)Lp;
             if (place) {
@@ -575,26 +575,6 @@ void build_plan(dsb_ctx* ctx, ForwardPlan& plan, int64_t cap, cudaStream_t s) {
   DSB_CUDA(cudaStreamSynchronize(s));
   plan.cap = cap;
 }
-
-struct Timer {       // optional CUDA-event bracket around one launch
-  dsb_ctx* ctx;
-  cudaStream_t s;
-  bool on;
-  Profiler::Rec rec;
-  Timer(dsb_ctx* c, cudaStream_t st, int cls, double flops) : ctx(c), s(st), on(c->prof.enabled) {
-    if (!on) return;
-    rec.a = c->prof.get();
-    rec.b = c->prof.get();
-    rec.cls = cls;
-    rec.flops = flops;
-    cudaEventRecord(rec.a, s);
-  }
-  ~Timer() {
-    if (!on) return;
-    cudaEventRecord(rec.b, s);
-    ctx->prof.recs.push_back(rec);
-  }
-};
 
 template <class T, bool SPLIT>
 void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, const float* means, const float* stds,

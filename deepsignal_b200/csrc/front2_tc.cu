@@ -180,9 +180,10 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
         for (int k = 0; k < 11; ++k) {
           const int j = j0 + k;
           const float x = (j >= 0 && j < p.S) ? __ldg(sig + j) : 0.f;
-          const float xc = fminf(fmaxf(x, -65504.f), 65504.f);      // fp16 parts (also in bf16 mode: 2^-22 instead of 2^-16)
-          const uint16_t xh = to16<true>(xc);
-          const uint16_t xl = to16<true>(xc - from16<true>(xh));
+          // fp16 parts (also in bf16 mode: 2^-22 instead of 2^-16).  |x| > 65504 becomes inf / NaN on purpose: it reaches the
+          // head kernel's non-finite check (DSB_ERR_NONFINITE) instead of being clamped into a silent wrong answer.
+          const uint16_t xh = to16<true>(x);
+          const uint16_t xl = to16<true>(x - from16<true>(xh));
           h[k] = xh; h[11 + k] = xl; h[22 + k] = xh;
         }
       }
@@ -234,7 +235,7 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
           for (int e = 0; e < 2; ++e) {
             const int c = 2 * k + e;
             const float m = fmaxf(ok0 ? __uint_as_float(a0[c]) : NEG, fmaxf(ok1 ? __uint_as_float(a1[c]) : NEG, ok2 ? __uint_as_float(a2[c]) : NEG));
-            v[e] = (ok0 || ok1 || ok2) ? fmaxf(m + p.b1v[cg * 16 + c], 0.f) : 0.f;
+            v[e] = (ok0 || ok1 || ok2) ? relu_keep_nan(m + p.b1v[cg * 16 + c]) : 0.f;
           }
           pk[k] = pack16<F16>(v[0], v[1]);
         }
@@ -279,8 +280,8 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int e = c * 8 + 2 * k;
-            float a = fmaxf(__uint_as_float(r2[e >> 4][e & 15]) + p.b2v[kb * 32 + e], 0.f);
-            float d = fmaxf(__uint_as_float(r2[(e + 1) >> 4][(e + 1) & 15]) + p.b2v[kb * 32 + e + 1], 0.f);
+            float a = relu_keep_nan(__uint_as_float(r2[e >> 4][e & 15]) + p.b2v[kb * 32 + e]);
+            float d = relu_keep_nan(__uint_as_float(r2[(e + 1) >> 4][(e + 1) & 15]) + p.b2v[kb * 32 + e + 1]);
             if (zero) { a = 0.f; d = 0.f; }
             pk[k] = pack16<F16>(a, d);
           }
@@ -327,7 +328,7 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
 #pragma unroll
           for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r2[h2][k]) + p.b3v[nh * 128 + col + k];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = halo ? 0.f : fmaxf(v[k], 0.f);
+          for (int k = 0; k < 16; ++k) v[k] = halo ? 0.f : relu_keep_nan(v[k]);
 #pragma unroll
           for (int k = 0; k < 8; ++k) pk[8 * h2 + k] = pack16<F16>(v[2 * k], v[2 * k + 1]);
         }

@@ -206,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const GemmTCParams p, const 
             }
             if ((e.relu_mask >> (col >> 4)) & 1u) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+              for (int i = 0; i < 16; ++i) v[i] = relu_keep_nan(v[i]);
             }
             if (halo) {
 #pragma unroll

@@ -312,7 +312,7 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const __grid_constant_
           for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(rr[h2][k]) + p.biasv[col + k];
           if (g < 6) {                                    // the residual stem (g6, g7) keeps its sign
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
+            for (int k = 0; k < 16; ++k) v[k] = relu_keep_nan(v[k]);
           }
           if (halo) {
 #pragma unroll
@@ -564,8 +564,8 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int e = e0 + 2 * k;
-            float a = fmaxf(__uint_as_float(rr[e >> 4][e & 15]) + bv[2 * k], 0.f);
-            float b = fmaxf(__uint_as_float(rr[(e + 1) >> 4][(e + 1) & 15]) + bv[2 * k + 1], 0.f);
+            float a = relu_keep_nan(__uint_as_float(rr[e >> 4][e & 15]) + bv[2 * k]);
+            float b = relu_keep_nan(__uint_as_float(rr[(e + 1) >> 4][(e + 1) & 15]) + bv[2 * k + 1]);
             if (zero) { a = 0.f; b = 0.f; }
             pk[k] = pack16<F16>(a, b);
             if constexpr (SPLIT) pl[k] = pack_lo(a, b, pk[k]);
@@ -652,7 +652,7 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const __grid_constant_
             }
           }
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = halo ? 0.f : fmaxf(v[k], 0.f);
+          for (int k = 0; k < 16; ++k) v[k] = halo ? 0.f : relu_keep_nan(v[k]);
 #pragma unroll
           for (int k = 0; k < 8; ++k) pk[8 * h2 + k] = pack16<F16>(v[2 * k], v[2 * k + 1]);
           if constexpr (SPLIT) {

@@ -56,6 +56,10 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// ReLU that keeps NaN (fmaxf(NaN, 0) is 0): an overflowed 16-bit activation (inf, then inf - inf) must reach the head
+// kernel's non-finite check instead of being laundered into a finite wrong answer.
+__device__ __forceinline__ float relu_keep_nan(float v) { return v < 0.f ? 0.f : v; }
+
 // exact-ish activations for the fp32 path, MUFU-based ones for the bf16 path
 template <bool FAST> __device__ __forceinline__ float act_tanh(float x) {
   if constexpr (FAST) {

@@ -151,7 +151,7 @@ class Engine(object):
 
     def profile(self):
         out = {}
-        for cls, name in enumerate(("gemm", "lstm_gemm", "elementwise", "incept_a")):
+        for cls, name in enumerate(_lib.PROFILE_CLASSES):
             ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
             self._check(self.lib.dsb_get_profile(self.h, cls, C.byref(ms), C.byref(n), C.byref(fl)))
             out[name] = dict(ms=ms.value, launches=n.value, flops=fl.value)
@@ -189,9 +189,20 @@ class Engine(object):
         mb, nm, ml = self._motif_bytes(motif_seqs)
         prm = _lib.ExtractParams(int(kmer_len), int(signal_len), {"mad": 0, "zscore": 1}[normalize_method],
                                  int(mod_loc), nm, ml, mb)
-        if capacity is None:
-            capacity = max(1, int(self.lib.dsb_extract_max_sites(C.byref(rd))))
         K, S = int(kmer_len), int(signal_len)
+        if capacity is None:
+            # Targeted sites are a few per cent of the bases (CpG: 1-2 %), while the hard upper bound — every event — would
+            # cost ~5 KB of output buffer per BASE on host and device.  Start from 4 % and, if the library reports
+            # DSB_ERR_CAPACITY (it returns the exact count), run again with exactly that many rows.
+            n_ev = max(1, int(self.lib.dsb_extract_max_sites(C.byref(rd))))
+            try:
+                return self.extract(reads, motif_seqs, mod_loc, kmer_len, signal_len, normalize_method, want64,
+                                    capacity=min(n_ev, max(1024, n_ev // 25)))
+            except DsbError as e:
+                if e.code != _lib.DSB_ERR_CAPACITY:
+                    raise
+                return self.extract(reads, motif_seqs, mod_loc, kmer_len, signal_len, normalize_method, want64,
+                                    capacity=e.n_sites)
         out = dict(
             site_read=np.empty(capacity, np.int32), site_loc=np.empty(capacity, np.int32),
             pos=np.empty(capacity, np.int64), pos_in_strand=np.empty(capacity, np.int64),
@@ -211,6 +222,10 @@ class Engine(object):
         scale = np.empty(R, np.float64)
         rc = self.lib.dsb_extract_host(self.h, C.byref(rd), C.byref(prm), C.byref(st), C.byref(n_sites),
                                        _ptr(shift), _ptr(scale))
+        if rc == _lib.DSB_ERR_CAPACITY:
+            err = DsbError(rc, (self.lib.dsb_last_error(self.h) or b"").decode())
+            err.n_sites = int(n_sites.value)
+            raise err
         self._check(rc)
         n = int(n_sites.value)
         res = {k: v[:n] for k, v in out.items()}

@@ -133,9 +133,11 @@ DSB_API int dsb_forward_host(dsb_ctx* ctx, int32_t precision, int64_t n,
  * stream has been synchronised. */
 DSB_API int dsb_nonfinite_count(dsb_ctx* ctx, int64_t* count);
 
-/* Per-kernel-class timing of the most recent profiled forward (CUDA events on the launch
- * stream around every launch of the class).  classes: 0 tensor-core GEMM kernels other than 1 and 3,
- * 1 LSTM kernel(s), 2 elementwise helpers, 3 inception kernel A (the largest share of a step). */
+/* Per-kernel-class timing of the calls made since profiling was switched on (CUDA events on the launch
+ * stream around every launch of the class; the forward runs single-stream while profiling).  Classes:
+ * 0 generic tensor-core / fp32 GEMM launches, 1 LSTM kernel(s), 2 elementwise helpers (pools, feature rows, head),
+ * 3 inception kernel A, 4 inception kernel B, 5 fused front end (conv1..conv3);
+ * extraction chain: 6 read_norm, 7 site count / scan / emit / mark, 8 LUT, 9 base_stats, 10 site_feature. */
 DSB_API int dsb_set_profiling(dsb_ctx* ctx, int32_t enabled);
 DSB_API int dsb_get_profile(dsb_ctx* ctx, int32_t cls, double* ms_total, int64_t* launches, double* flops);
 DSB_API int64_t dsb_launch_count(const dsb_ctx* ctx);   /* kernels launched by this ctx so far */
