@@ -9,9 +9,10 @@ by one call into libdsb200 (``Engine.forward`` -> ``dsb_forward_host``); nothing
 hot path is computed in Python.
 
 Differences that are deliberate:
-* one reader thread + one GPU worker per device instead of N TensorFlow processes
-  (the reference's process fan-out exists to use CPU cores; the GPU engine is fed by
-  large batches instead).  ``--nproc`` is accepted and only bounds host parsing threads.
+* one reader thread + one GPU worker (thread + ``dsb_ctx``) per device instead of N TensorFlow
+  processes (the reference's process fan-out exists to use CPU cores; the GPU engine is fed by
+  large batches instead); ``--devices 0,1,...`` or ``torchrun`` shard the reads over several GPUs
+  (deepsignal_b200/parallel.py).  ``--nproc`` is accepted and only bounds host parsing threads.
 * a features batch is forwarded in one call rather than in ``batch_size`` slices: the model is
   in inference mode, so results are batch-composition invariant; ``batch_num`` is still
   reported as ceil(n / batch_size) like the reference.
@@ -132,50 +133,56 @@ def _load_engine(model_path, kmer_len, cent_signals_len, is_cnn, is_rnn, is_base
     return eng
 
 
-def _features_batches_from_reads(reads_path, engine, f5_args, kmer_len, cent_signals_len):
-    """fast5-directory mode of the reference (:94-122) on packed reads: extraction on the GPU,
-    7-tuples out, grouped by ``f5_batch_num`` reads."""
-    from .extract_features import load_reads, extract_batch_arrays
-    (_, _, _, reference_path, is_dna, normalize_method, motifs, mod_loc, methy_label, f5_batch_num,
-     position_file) = f5_args
-    motif_seqs = get_motif_seqs(motifs, is_dna)
+def _read_batches(reads_path, f5_args):
+    """fast5-directory mode of the reference (:94-122,437-457) on packed reads / fast5 files: yields ReadBatch slices of
+    ``f5_batch_num * 64`` reads (the reference hands ``f5_batch_num`` files to each CPU worker, :104-108)."""
+    from .extract_features import load_reads
+    (is_recursive, corrected_group, basecall_subgroup, reference_path, is_dna, normalize_method, motifs, mod_loc,
+     methy_label, f5_batch_num, position_file) = f5_args
     chrom2len = get_contig2len(reference_path) if reference_path is not None else None
-    positions = None
-    if position_file is not None:
-        from .extract_features import _read_position_file
-        positions = _read_position_file(position_file)
-    reads = load_reads(reads_path, chrom2len)
+    reads, errornum = load_reads(reads_path, chrom2len, is_recursive, corrected_group, basecall_subgroup,
+                                 return_errors=True)
     step = max(1, int(f5_batch_num)) * 64
-    for lo in range(0, reads.n_reads, step):
-        rb = reads.slice(lo, min(reads.n_reads, lo + step))
-        arr, info = extract_batch_arrays(engine, rb, motif_seqs, mod_loc, kmer_len, cent_signals_len,
-                                         normalize_method, positions)
-        labels = [methy_label] * len(info)
-        yield (info, arr["kmer"].tolist(), arr["means64"], arr["stds64"], arr["lens_i32"], arr["signals64"], labels)
+    spans = [(lo, min(reads.n_reads, lo + step)) for lo in range(0, reads.n_reads, step)]
+    return reads, spans, errornum
 
 
-def call_mods(input_path, model_path, result_file, kmer_len, cent_signals_len,
-              batch_size, learning_rate, class_num, nproc, is_gpu, is_rnn, is_base, is_cnn,
-              f5_args, precision="fp16x2", device=0):
-    """Same positional signature as the reference ``call_mods`` (:417-495) plus ``precision`` /
-    ``device``.  ``is_gpu`` is accepted for compatibility; this implementation always runs on the
-    GPU and fails loudly if none is present."""
-    start = time.time()
-    model_path = os.path.abspath(model_path)
-    input_path = os.path.abspath(input_path)
-    engine = _load_engine(model_path, kmer_len, cent_signals_len, is_cnn, is_rnn, is_base, device)
-    model = _ModelHandle(kmer_len, cent_signals_len, class_num, is_cnn, is_base, is_rnn, precision)
+class _Work(object):
+    """One unit of work for a device worker: kind in {"reads", "tuple", "block"} + payload."""
+    __slots__ = ("kind", "payload")
+
+    def __init__(self, kind, payload):
+        self.kind, self.payload = kind, payload
+
+
+def _process_work(engine, model, work, ctx):
+    """Runs on the worker that owns ``work``: (extraction +) forward + formatting.  Returns (lines, batch_num, errors)."""
+    if work.kind == "block":        # C++-parsed feature-file block -> forward -> C++-formatted result lines
+        from .fast_tsv import format_calls
+        block = work.payload
+        probs, prediction = engine.forward(block.kmer, block.means, block.stds, block.lens, block.signals,
+                                           precision=model.precision)
+        return [format_calls(block, probs, prediction).decode().rstrip("\n")], -(-block.n // ctx["batch_size"]), 0
+    if work.kind == "reads":        # packed reads -> extraction kernels -> forward, all on this worker's device
+        from .extract_features import extract_batch_arrays, failed_reads
+        arr, info = extract_batch_arrays(engine, work.payload, ctx["motif_seqs"], ctx["mod_loc"], ctx["kmer_len"],
+                                         ctx["cent_signals_len"], ctx["normalize_method"], ctx["positions"], want64=False)
+        errors = int(np.sum(failed_reads(arr)))
+        batch = (info, arr["kmer"], arr["means"], arr["stds"], arr["lens"], arr["signals"], [ctx["methy_label"]] * len(info))
+        pred_str, _, nb = _call_mods(batch, engine, model, ctx["learning_rate"], ctx["batch_size"])
+        return pred_str, nb, errors
+    pred_str, _, nb = _call_mods(work.payload, engine, model, ctx["learning_rate"], ctx["batch_size"])
+    return pred_str, nb, 0
+
+
+def _iter_work(input_path, kmer_len, cent_signals_len, nproc, f5_args, state):
+    """Work items of one call_mods run, in input order; ``state`` receives n_reads / n_failed for the final report."""
     f5_batch_num = f5_args[9]
-
-    pred_str_q = queue.Queue(maxsize=queen_size_border)
-    p_w = threading.Thread(target=_write_predstr_to_file, args=(result_file, pred_str_q), daemon=True)
-    p_w.start()
-    n_batches = 0
     if os.path.isdir(input_path) or input_path.endswith(".npz"):
-        for features_batch in _features_batches_from_reads(input_path, engine, f5_args, kmer_len, cent_signals_len):
-            pred_str, _, nb = _call_mods(features_batch, engine, model, learning_rate, batch_size)
-            pred_str_q.put(pred_str)
-            n_batches += nb
+        reads, spans, errornum = _read_batches(input_path, f5_args)
+        state["n_reads"], state["n_failed"], state["n_items"] = reads.n_reads + errornum, errornum, len(spans)
+        for lo, hi in spans:
+            yield _Work("reads", reads.slice(lo, hi))
     elif input_path.endswith(".bin"):
         # the reference's 1628-byte binary sample records (scripts/generate_binary_feature_file.py): no read / position
         # columns exist in that format, so the six info columns are printed as '.'
@@ -185,37 +192,123 @@ def call_mods(input_path, model_path, result_file, kmer_len, cent_signals_len,
         for lo in range(0, len(rec["labels"]), step):
             sl = slice(lo, lo + step)
             n_here = len(rec["labels"][sl])
-            batch = (["\t".join(["."] * 6)] * n_here, rec["kmer"][sl].tolist(), rec["means"][sl], rec["stds"][sl],
-                     rec["lens"][sl], rec["signals"][sl], rec["labels"][sl])
-            pred_str, _, nb = _call_mods(batch, engine, model, learning_rate, batch_size)
-            pred_str_q.put(pred_str)
-            n_batches += nb
+            yield _Work("tuple", (["\t".join(["."] * 6)] * n_here, rec["kmer"][sl], rec["means"][sl], rec["stds"][sl],
+                                  rec["lens"][sl], rec["signals"][sl], rec["labels"][sl]))
     elif os.environ.get("DSB_PY_TSV", "0") != "1":
         # fast path: C++ text codec (csrc/tsv.cpp); identical parsing rules and byte-identical result lines
-        from .fast_tsv import iter_feature_blocks, format_calls
+        from .fast_tsv import iter_feature_blocks
         for block in iter_feature_blocks(input_path, kmer_len, cent_signals_len, nthreads=max(1, nproc)):
-            probs, prediction = engine.forward(block.kmer, block.means, block.stds, block.lens, block.signals,
-                                               precision=model.precision)
-            pred_str_q.put([format_calls(block, probs, prediction).decode().rstrip("\n")])
-            n_batches += -(-block.n // batch_size)
+            yield _Work("block", block)
     else:
         features_batch_q = queue.Queue(maxsize=queen_size_border)
-        p_rf = threading.Thread(target=_read_features_file, args=(input_path, features_batch_q, f5_batch_num * 64),
-                                daemon=True)
+
+        def reader():       # a malformed line (e.g. a base outside ACGTN, reference :52) must fail the run, not hang it
+            try:
+                _read_features_file(input_path, features_batch_q, f5_batch_num * 64)
+            except BaseException as e:      # noqa: BLE001 - re-raised by the consumer below
+                features_batch_q.put(e)
+        p_rf = threading.Thread(target=reader, daemon=True)
         p_rf.start()
         while True:
             features_batch = features_batch_q.get()
+            if isinstance(features_batch, BaseException):
+                raise features_batch
             if isinstance(features_batch, str) and features_batch == "kill":
                 break
-            pred_str, _, nb = _call_mods(features_batch, engine, model, learning_rate, batch_size)
-            pred_str_q.put(pred_str)
-            n_batches += nb
+            yield _Work("tuple", features_batch)
         p_rf.join()
-    pred_str_q.put("kill")
-    p_w.join()
-    engine.close()
-    print("call_mods process {} ending, proceed {} batches".format(os.getpid(), n_batches))
-    print("call_mods costs %.2f seconds.." % (time.time() - start))
+
+
+def call_mods(input_path, model_path, result_file, kmer_len, cent_signals_len,
+              batch_size, learning_rate, class_num, nproc, is_gpu, is_rnn, is_base, is_cnn,
+              f5_args, precision="fp16x2", device=0, devices=None):
+    """Same positional signature as the reference ``call_mods`` (:417-495) plus ``precision`` / ``device`` /
+    ``devices``.  ``is_gpu`` is accepted for compatibility; this implementation always runs on the GPU and fails
+    loudly if none is present.
+
+    Reads are independent, so the work shards with no collective (reference fan-out: :461-476):
+    ``devices=[0, 1, ...]`` runs one worker thread + engine per GPU in this process; under ``torchrun``
+    (WORLD_SIZE > 1) every rank handles the batches it owns on ``cuda:LOCAL_RANK`` and rank 0 writes the file.
+    Either way the result file is byte-identical to a single-GPU run: lines keep input order, each read's lines
+    stay contiguous, and per-sample results do not depend on batch composition (inference-mode graph)."""
+    from . import parallel
+    start = time.time()
+    model_path = os.path.abspath(model_path)
+    input_path = os.path.abspath(input_path)
+    model = _ModelHandle(kmer_len, cent_signals_len, class_num, is_cnn, is_base, is_rnn, precision)
+    (_, _, _, _, is_dna, normalize_method, motifs, mod_loc, methy_label, f5_batch_num, position_file) = f5_args
+    positions = None
+    if position_file is not None:
+        from .extract_features import _read_position_file
+        positions = _read_position_file(position_file)
+    ctx = dict(batch_size=batch_size, learning_rate=learning_rate, kmer_len=kmer_len, cent_signals_len=cent_signals_len,
+               motif_seqs=get_motif_seqs(motifs, is_dna), mod_loc=mod_loc, normalize_method=normalize_method,
+               positions=positions, methy_label=methy_label)
+    state = {"n_reads": 0, "n_failed": 0, "n_items": None}
+    rank, local_rank, world_size = parallel.world()
+    devices = [int(d) for d in devices] if devices else [local_rank if world_size > 1 else int(device)]
+    make_engine = lambda w: _load_engine(model_path, kmer_len, cent_signals_len, is_cnn, is_rnn, is_base, devices[w])
+    counters = {"batches": 0, "errors": 0}
+
+    if world_size > 1:
+        # ---- one process per GPU (torchrun): own batches round-robin, rank 0 gathers the text and writes it
+        import torch.distributed as dist
+        own_group = not dist.is_initialized()
+        if own_group:
+            dist.init_process_group(backend="gloo")
+        engine = make_engine(0)
+        local, stats = [], [0, 0]
+        work_iter = _iter_work(input_path, kmer_len, cent_signals_len, nproc, f5_args, state)
+        for i, work in enumerate(work_iter):
+            owner = (parallel.range_owner(i, state["n_items"], world_size) if state["n_items"] is not None
+                     else parallel.batch_owner(i, world_size))
+            if owner != rank:
+                continue
+            lines, nb, err = _process_work(engine, model, work, ctx)
+            local.append((i, lines))
+            stats[0] += nb
+            stats[1] += err
+        engine.close()
+        merged = parallel.gather_in_order(local, rank, world_size)
+        all_stats = [None] * world_size
+        dist.all_gather_object(all_stats, stats)
+        counters["batches"] = sum(s[0] for s in all_stats)
+        counters["errors"] = sum(s[1] for s in all_stats)
+        if rank == 0:
+            with open(result_file, "w") as wf:
+                for lines in merged:
+                    for one in lines:
+                        wf.write(one + "\n")
+        if own_group:
+            dist.barrier()
+            dist.destroy_process_group()
+    else:
+        # ---- one worker thread + engine per device in this process; the writer keeps input order
+        pred_str_q = queue.Queue(maxsize=queen_size_border)
+        p_w = threading.Thread(target=_write_predstr_to_file, args=(result_file, pred_str_q), daemon=True)
+        p_w.start()
+
+        def emit(res):
+            lines, nb, err = res
+            pred_str_q.put(lines)
+            counters["batches"] += nb
+            counters["errors"] += err
+
+        nw = len(devices)
+        items = _iter_work(input_path, kmer_len, cent_signals_len, nproc, f5_args, state)
+
+        def owner(i):
+            return parallel.range_owner(i, state["n_items"], nw) if state["n_items"] is not None else parallel.batch_owner(i, nw)
+        try:
+            parallel.run_sharded(items, nw, owner, make_engine, lambda eng, work: _process_work(eng, model, work, ctx), emit)
+        finally:
+            pred_str_q.put("kill")
+            p_w.join()
+    if rank == 0:
+        if state["n_reads"]:
+            print("%d of %d fast5 files failed.." % (state["n_failed"] + counters["errors"], state["n_reads"]))
+        print("call_mods process {} ending, proceed {} batches".format(os.getpid(), counters["batches"]))
+        print("call_mods costs %.2f seconds.." % (time.time() - start))
 
 
 def main():

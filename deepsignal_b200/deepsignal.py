@@ -33,7 +33,8 @@ def main_call_mods(args):
     call_mods(args.input_path, args.model_path, args.result_file, args.kmer_len, args.cent_signals_len,
               args.batch_size, args.learning_rate, args.class_num, args.nproc, str2bool(args.is_gpu),
               str2bool(args.is_rnn), str2bool(args.is_base), str2bool(args.is_cnn), f5_args,
-              precision=args.precision, device=args.device)
+              precision=args.precision, device=args.device,
+              devices=[int(d) for d in args.devices.split(",")] if args.devices else None)
 
 
 def _fast5_flags(g, with_label):
@@ -128,6 +129,10 @@ def main():
     sc.add_argument("--is_gpu", action="store", type=str, default="no", required=False, choices=["yes", "no"],
                     help="accepted for compatibility: this engine always runs on the GPU")
     sc.add_argument("--device", type=int, default=0, help="CUDA device index")
+    sc.add_argument("--devices", type=str, default=None,
+                    help="comma-separated CUDA device indices: shard the reads over several GPUs of this box "
+                         "(one worker + engine per device, no collective; the result file is identical to a 1-GPU run). "
+                         "Under torchrun every rank uses cuda:LOCAL_RANK instead.")
     sc.set_defaults(func=main_call_mods)
 
     args = parser.parse_args()

@@ -72,15 +72,22 @@ def _reads_from_fast5s(fast5_files, corrected_group, basecall_subgroup):
                 al = grp["Alignment"].attrs
                 dec = lambda v: v.decode() if isinstance(v, bytes) else str(v)
                 ch = h5["UniqueGlobalKey/channel_id"].attrs
-                rows.append((dec(al["mapped_chrom"]), int(al["mapped_start"]), dec(al["mapped_strand"]), read_id,
-                             "t" if basecall_subgroup.endswith("template") else "c",
-                             float(ch["range"]) / float(ch["digitisation"]), float(ch["offset"])))
-                raws.append(raw)
-                ev_s.append(np.asarray(ev["start"], dtype=np.int64) + rel)
-                ev_l.append(np.asarray(ev["length"], dtype=np.int64))
-                ev_b.append(np.frombuffer(b"".join(bytes(x) for x in ev["base"]), dtype=np.uint8))
+                row = (dec(al["mapped_chrom"]), int(al["mapped_start"]), dec(al["mapped_strand"]), read_id,
+                       "t" if basecall_subgroup.endswith("template") else "c",
+                       float(ch["range"]) / float(ch["digitisation"]), float(ch["offset"]))
+                starts = np.asarray(ev["start"], dtype=np.int64) + rel
+                lengths = np.asarray(ev["length"], dtype=np.int64)
+                bases = np.frombuffer(b"".join(bytes(x) for x in ev["base"]), dtype=np.uint8)
+                if not (len(starts) == len(lengths) == len(bases)):
+                    raise ValueError("Events columns differ in length")
         except Exception:
             errors += 1
+        else:       # every field of the read parsed: only now do the per-read lists grow (they must stay aligned)
+            rows.append(row)
+            raws.append(raw)
+            ev_s.append(starts)
+            ev_l.append(lengths)
+            ev_b.append(bases)
     n = len(raws)
     off = lambda parts: np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int64)
     cat = lambda parts, dt: (np.concatenate(parts).astype(dt) if n else np.zeros(0, dt))
@@ -132,18 +139,30 @@ def _read_position_file(position_file):
     return postions
 
 
+def failed_reads(arr):
+    """Reads the extraction could not normalise: no raw samples / non-positive scaling (the kernels emit no sites for
+    them) or a zero / non-finite scale (MAD = 0 on a constant signal: numpy would print inf / nan features).  They
+    count as errors and contribute no features, like a read the reference's try/except drops (:281-283)."""
+    sc = arr["read_scale"]
+    return ~np.isfinite(sc) | (sc == 0)
+
+
 def extract_batch_arrays(engine, reads, motif_seqs, methyloc, kmer_len, raw_signals_len, normalize_method,
-                         positions=None):
-    """GPU extraction of one read batch -> (arrays dict, sampleinfo strings); applies --positions."""
+                         positions=None, want64=True):
+    """GPU extraction of one read batch -> (arrays dict, sampleinfo strings); applies --positions.
+    ``want64=False`` skips the float64 copies that only the feature-file text needs (call_mods feeds float32)."""
     if kmer_len % 2 == 0:
         raise ValueError("kmer_len must be odd")
     arr = engine.extract(reads, motif_seqs, mod_loc=methyloc, kmer_len=kmer_len, signal_len=raw_signals_len,
-                         normalize_method=normalize_method, want64=True)
+                         normalize_method=normalize_method, want64=want64)
     n = arr["n_sites"]
     strand = np.where(reads.strand_minus[arr["site_read"]] != 0, "-", "+") if n else np.zeros(0, "<U1")
+    bad_read = failed_reads(arr)
     info, keep = [], []
     for i in range(n):
         r = int(arr["site_read"][i])
+        if bad_read[r]:
+            continue
         chrom, pos = reads.chrom[r], int(arr["pos"][i])
         if positions is not None and key_sep.join([chrom, str(pos), str(strand[i])]) not in positions:
             continue
@@ -177,7 +196,7 @@ def _extract_features(reads, corrected_group, basecall_subgroup, normalize_metho
     finally:
         if own:
             engine.close()
-    error = int(np.sum(~np.isfinite(arr["read_scale"])))
+    error = int(np.sum(failed_reads(arr)))
     code2base = "ACGTN"
     features_list = []
     for i in range(arr["n_sites"]):

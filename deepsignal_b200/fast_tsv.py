@@ -21,9 +21,13 @@ class FeatureBlock(object):
         return [t[o + s:o + e].decode() for s, e in self.info_off]
 
 
-def iter_feature_blocks(path, kmer_len=17, signal_len=360, max_samples=1 << 18, nthreads=None, block_bytes=None):
+BLOCK_SAMPLES = 1 << 18     # samples per parsed block = per forward call of call_mods
+
+
+def iter_feature_blocks(path, kmer_len=17, signal_len=360, max_samples=None, nthreads=None, block_bytes=None):
     lib = _lib.load()
     nthreads = nthreads or min(32, os.cpu_count() or 1)
+    max_samples = max_samples or BLOCK_SAMPLES
     block_bytes = block_bytes or max(1 << 20, int(max_samples * (signal_len * 11 + kmer_len * 30 + 256)))
     K, S = int(kmer_len), int(signal_len)
     carry = b""

@@ -250,3 +250,108 @@ def test_site_frequency_matches_reference_script(tmp_path):
         out = str(tmp_path / (tag + ".txt"))
         cmf.write_sitekey2stats(stats, out, srt, bed)
         assert open(out).read() == ref[tag], tag
+
+
+# ---------------------------------------------------------------------------------------------------------
+# read sharding in the product entry point (call_modifications.call_mods): the multi-worker result file must be
+# byte-identical to the single-worker one.  The engine is replaced by a deterministic stand-in (no GPU here).
+# ---------------------------------------------------------------------------------------------------------
+class _StubEngine(object):
+    def __init__(self, device):
+        self.device = device
+
+    def forward(self, kmer, means, stds, lens, signals, precision="fp16x2"):
+        z = (np.asarray(means, np.float32).sum(axis=1) + np.asarray(signals, np.float32)[:, :8].sum(axis=1)
+             + np.asarray(lens, np.float32).sum(axis=1) * 0.01)
+        p1 = (1.0 / (1.0 + np.exp(-z))).astype(np.float32)
+        probs = np.stack([np.float32(1.0) - p1, p1], axis=1).astype(np.float32)
+        return probs, np.argmax(probs, axis=1).astype(np.int32)
+
+    def close(self):
+        pass
+
+
+def _f5_args(f5_batch_num=1):
+    return (True, "RawGenomeCorrected_000", "BaseCalled_template", None, True, "mad", "CG", 0, 1, f5_batch_num, None)
+
+
+def _run_call_mods(tsv, out, devices=None, py_tsv=False):
+    os.environ["DSB_PY_TSV"] = "1" if py_tsv else "0"
+    try:
+        cm.call_mods(tsv, "unused.ckpt", out, 17, 360, 512, 0.001, 2, 2, False, True, True, True, _f5_args(), devices=devices)
+    finally:
+        os.environ.pop("DSB_PY_TSV", None)
+    return open(out).read()
+
+
+@pytest.mark.parametrize("py_tsv", [False, True])
+def test_call_mods_devices_sharding_is_byte_identical(tmp_path, monkeypatch, py_tsv):
+    from deepsignal_b200.synth import synth_features, write_feature_tsv
+    monkeypatch.setattr(cm, "_load_engine", lambda model_path, k, s, c, r, b, device=0: _StubEngine(device))
+    monkeypatch.setattr("deepsignal_b200.fast_tsv.BLOCK_SAMPLES", 128)
+    tsv = str(tmp_path / "f.tsv")
+    write_feature_tsv(tsv, synth_features(1500, seed=5, sites_per_read=7))
+    one = _run_call_mods(tsv, str(tmp_path / "one.tsv"), None, py_tsv)
+    assert len(one.splitlines()) == 1500
+    for devs in ([0, 1], [0, 1, 2, 3, 4, 5, 6, 7]):
+        many = _run_call_mods(tsv, str(tmp_path / "many.tsv"), devs, py_tsv)
+        assert many == one, devs
+    # each read's lines stay contiguous and in input order
+    names = [ln.split("\t")[4] for ln in one.splitlines()]
+    assert names == sorted(names)
+
+
+def test_call_mods_worker_error_propagates(tmp_path, monkeypatch):
+    from deepsignal_b200.synth import synth_features, write_feature_tsv
+
+    class Boom(_StubEngine):
+        def forward(self, *a, **k):
+            raise RuntimeError("device fell over")
+    monkeypatch.setattr(cm, "_load_engine", lambda model_path, k, s, c, r, b, device=0: Boom(device))
+    tsv = str(tmp_path / "f.tsv")
+    write_feature_tsv(tsv, synth_features(60, seed=5, sites_per_read=7))
+    with pytest.raises(RuntimeError, match="device fell over"):
+        _run_call_mods(tsv, str(tmp_path / "o.tsv"), [0, 1])
+
+
+def test_feature_file_with_non_acgtn_kmer_is_rejected(tmp_path, monkeypatch):
+    """reference call_modifications.py:52: base2code_dna[x] raises KeyError on a base outside ACGTN."""
+    from deepsignal_b200.synth import synth_features, write_feature_tsv
+    monkeypatch.setattr(cm, "_load_engine", lambda model_path, k, s, c, r, b, device=0: _StubEngine(device))
+    tsv = str(tmp_path / "f.tsv")
+    write_feature_tsv(tsv, synth_features(8, seed=5))
+    txt = open(tsv).read().splitlines()
+    w = txt[3].split("\t")
+    w[6] = w[6][:5] + "X" + w[6][6:]
+    txt[3] = "\t".join(w)
+    open(tsv, "w").write("\n".join(txt) + "\n")
+    with pytest.raises((KeyError, ValueError)):
+        _run_call_mods(tsv, str(tmp_path / "o.tsv"), None, py_tsv=True)
+    with pytest.raises((KeyError, ValueError)):
+        _run_call_mods(tsv, str(tmp_path / "o2.tsv"), None, py_tsv=False)
+
+
+def _gloo_call_mods_worker(rank, world_size, port, tsv, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world_size))
+    from deepsignal_b200 import call_modifications as cm2
+    cm2._load_engine = lambda model_path, k, s, c, r, b, device=0: _StubEngine(device)
+    cm2.call_mods(tsv, "unused.ckpt", out, 17, 360, 512, 0.001, 2, 2, False, True, True, True, _f5_args())
+
+
+def test_call_mods_two_rank_process_sharding_is_byte_identical(tmp_path, monkeypatch):
+    """torchrun-style: two ranks over gloo, rank 0 writes; same bytes as the single-process run."""
+    import socket
+    import torch.multiprocessing as mp
+    from deepsignal_b200.synth import synth_features, write_feature_tsv
+    monkeypatch.setattr(cm, "_load_engine", lambda model_path, k, s, c, r, b, device=0: _StubEngine(device))
+    tsv = str(tmp_path / "f.tsv")
+    write_feature_tsv(tsv, synth_features(900, seed=6, sites_per_read=9))
+    one = _run_call_mods(tsv, str(tmp_path / "one.tsv"))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "two.tsv")
+    mp.spawn(_gloo_call_mods_worker, args=(2, port, tsv, out), nprocs=2, join=True)
+    assert open(out).read() == one
