@@ -8,9 +8,13 @@ The reference restores ``bn_17.sn_360.epoch_N.ckpt`` with ``tf.train.Saver().res
 Format restated from the published TensorFlow sources (tensorflow/core/util/tensor_bundle/, core/lib/io/
 table format = LevelDB's): data blocks of prefix-compressed entries + restart array, each followed by a
 1-byte compression type and a masked crc32c; a 48-byte footer with the metaindex / index block handles and the
-magic 0xdb4775248b80fb57.  TensorFlow is not installable here and no real checkpoint is reachable, so this
-module is verified only by a write→read round trip and hand-built blocks (PARITY UNPINNED against a TF-written
-file).  Snappy-compressed blocks (type 1) are rejected with a clear error; TF writes bundle indexes uncompressed.
+magic 0xdb4775248b80fb57.  Blocks may be stored raw (type 0) or Snappy-compressed (type 1: TF's table builder
+compresses a block when that saves >= 12.5 %, which an index full of repetitive variable names usually does), so the
+reader carries a pure-Python decoder of the Snappy raw format (varint length, then literal / copy elements) and
+verifies every block's masked crc32c.  TensorFlow is not installable here and no real checkpoint is reachable, so this
+module is verified by write->read round trips (raw and compressed, prefix-shared keys, multi-block indexes), by
+hand-assembled Snappy streams from the format description and by a second, bitwise crc32c implementation in the
+tests: PARITY UNPINNED against a TF-written file.
 """
 from __future__ import annotations
 
@@ -95,11 +99,90 @@ def _parse_entry(val):
     return e
 
 
-def _read_block(data, offset, size):
+def _crc32c_table():
+    tab = []
+    for i in range(256):
+        c = i
+        for _ in range(8):
+            c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+        tab.append(c)
+    return tab
+
+
+_CRC_TAB = _crc32c_table()
+
+
+def crc32c(data, crc=0):
+    crc ^= 0xFFFFFFFF
+    for b in data:
+        crc = _CRC_TAB[(crc ^ b) & 0xFF] ^ (crc >> 8)
+    return crc ^ 0xFFFFFFFF
+
+
+def _mask(crc):
+    return ((((crc >> 15) | (crc << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def snappy_decompress(buf):
+    """Snappy raw format (the block format, not the framing format): varint uncompressed length, then elements whose
+    tag byte's low two bits select literal (00), copy with 1-byte offset (01), 2-byte offset (10), 4-byte offset (11)."""
+    n, pos = _varint(buf, 0)
+    out = bytearray()
+    end = len(buf)
+    while pos < end:
+        tag = buf[pos]
+        pos += 1
+        kind = tag & 3
+        if kind == 0:
+            ln = tag >> 2
+            if ln >= 60:
+                nb = ln - 59
+                ln = int.from_bytes(buf[pos:pos + nb], "little")
+                pos += nb
+            ln += 1
+            if pos + ln > end:
+                raise ValueError("snappy: literal runs past the end of the block")
+            out += buf[pos:pos + ln]
+            pos += ln
+            continue
+        if kind == 1:
+            ln = 4 + ((tag >> 2) & 7)
+            off = ((tag >> 5) << 8) | buf[pos]
+            pos += 1
+        elif kind == 2:
+            ln = 1 + (tag >> 2)
+            off = buf[pos] | (buf[pos + 1] << 8)
+            pos += 2
+        else:
+            ln = 1 + (tag >> 2)
+            off = int.from_bytes(buf[pos:pos + 4], "little")
+            pos += 4
+        if off == 0 or off > len(out):
+            raise ValueError("snappy: copy offset {} outside the {} bytes produced so far".format(off, len(out)))
+        start = len(out) - off
+        if off >= ln:
+            out += out[start:start + ln]
+        else:                               # overlapping copy: the pattern repeats
+            for i in range(ln):
+                out.append(out[start + i])
+    if len(out) != n:
+        raise ValueError("snappy: produced {} bytes, header says {}".format(len(out), n))
+    return bytes(out)
+
+
+def _read_block(data, offset, size, verify=True):
+    if offset + size + 5 > len(data):
+        raise ValueError("SSTable block handle ({}, {}) points outside the file".format(offset, size))
     block = data[offset:offset + size]
     ctype = data[offset + size]
-    if ctype != 0:
-        raise ValueError("compressed SSTable block (type {}) is not supported".format(ctype))
+    if verify:
+        stored = struct.unpack_from("<I", data, offset + size + 1)[0]
+        if stored != _mask(crc32c(data[offset:offset + size + 1])):
+            raise ValueError("SSTable block at {} fails its crc32c check".format(offset))
+    if ctype == 1:
+        block = snappy_decompress(block)
+    elif ctype != 0:
+        raise ValueError("SSTable block compression type {} is not supported (0 = raw, 1 = snappy)".format(ctype))
     n_restarts = struct.unpack_from("<I", block, len(block) - 4)[0]
     limit = len(block) - 4 - 4 * n_restarts
     pos, key, out = 0, b"", []
@@ -157,42 +240,65 @@ def read_bundle(prefix, names=None):
 
 
 # ---- writer (tests / converting an .npz to a bundle) -------------------------------------------------------
-def _crc32c_table():
-    tab = []
-    for i in range(256):
-        c = i
-        for _ in range(8):
-            c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
-        tab.append(c)
-    return tab
-
-
-_CRC_TAB = _crc32c_table()
-
-
-def crc32c(data, crc=0):
-    crc ^= 0xFFFFFFFF
-    for b in data:
-        crc = _CRC_TAB[(crc ^ b) & 0xFF] ^ (crc >> 8)
-    return crc ^ 0xFFFFFFFF
-
-
-def _mask(crc):
-    return ((((crc >> 15) | (crc << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
-
-
-def _block(entries):
+def _block(entries, restart_interval=16):
+    """LevelDB block: entries with keys prefix-compressed against the previous key, a full key every
+    ``restart_interval`` entries (TF / LevelDB default 16), then the restart offsets and their count."""
     out = bytearray()
-    for k, v in entries:                     # restart interval 1: no prefix sharing (valid, just not compact)
-        out += _put_varint(0) + _put_varint(len(k)) + _put_varint(len(v)) + k + v
     restarts = []
-    pos = 0
-    for k, v in entries:
-        restarts.append(pos)
-        pos += len(_put_varint(0)) + len(_put_varint(len(k))) + len(_put_varint(len(v))) + len(k) + len(v)
+    prev = b""
+    for i, (k, v) in enumerate(entries):
+        if i % restart_interval == 0:
+            restarts.append(len(out))
+            shared = 0
+        else:
+            shared = 0
+            while shared < min(len(prev), len(k)) and prev[shared] == k[shared]:
+                shared += 1
+        out += _put_varint(shared) + _put_varint(len(k) - shared) + _put_varint(len(v)) + k[shared:] + v
+        prev = k
+    if not restarts:
+        restarts.append(0)
     for r in restarts:
         out += struct.pack("<I", r)
     out += struct.pack("<I", len(restarts))
+    return bytes(out)
+
+
+def snappy_compress(data):
+    """Small greedy Snappy encoder (4-byte hash matches, copies with 2-byte offsets, literals otherwise) used to write
+    compressed test bundles; any conforming decoder reads its output."""
+    out = bytearray(_put_varint(len(data)))
+    table = {}
+    pos = lit = 0
+    n = len(data)
+
+    def emit_literal(lo, hi):
+        while lo < hi:
+            ln = min(hi - lo, 1 << 16)
+            if ln <= 60:
+                out.append((ln - 1) << 2)
+            elif ln <= 256:
+                out.extend(bytes([60 << 2, ln - 1]))
+            else:
+                out.extend(bytes([61 << 2]) + struct.pack("<H", ln - 1))
+            out.extend(data[lo:lo + ln])
+            lo += ln
+
+    while pos + 4 <= n:
+        key = data[pos:pos + 4]
+        cand = table.get(key)
+        table[key] = pos
+        if cand is not None and pos - cand < 65536:
+            ln = 4
+            while pos + ln < n and ln < 64 and data[cand + ln] == data[pos + ln]:
+                ln += 1
+            emit_literal(lit, pos)
+            out.extend(bytes([((ln - 1) << 2) | 2]) + struct.pack("<H", pos - cand))
+            pos += ln
+            lit = pos
+        else:
+            pos += 1
+    emit_literal(lit, n)
     return bytes(out)
 
 
@@ -207,9 +313,10 @@ def _entry_proto(dtype, shape, offset, size, crc):
     return msg
 
 
-def write_bundle(prefix, tensors: dict):
+def write_bundle(prefix, tensors: dict, compress=False, block_entries=0):
     """Single-shard float32/int32 bundle with the TF file names; enough for round trips and for handing a
-    synthetic checkpoint to tools that expect the ``.ckpt`` prefix."""
+    synthetic checkpoint to tools that expect the ``.ckpt`` prefix.  ``compress`` stores the blocks Snappy-compressed
+    (type 1) like TF's table builder does when it pays; ``block_entries`` > 0 splits the entries over several data blocks."""
     data = bytearray()
     kv = []
     for name in sorted(tensors):
@@ -223,15 +330,23 @@ def write_bundle(prefix, tensors: dict):
 
     def add_block(entries):
         body = _block(entries)
+        ctype = b"\x00"
+        if compress:
+            body, ctype = snappy_compress(body), b"\x01"
         off = len(blocks)
         blocks.extend(body)
-        blocks.extend(b"\x00" + struct.pack("<I", _mask(crc32c(body + b"\x00"))))
+        blocks.extend(ctype + struct.pack("<I", _mask(crc32c(body + ctype))))
         return off, len(body)
 
-    d_off, d_size = add_block([(b"", header)] + kv)
+    all_entries = [(b"", header)] + kv
+    per = block_entries if block_entries > 0 else len(all_entries)
+    index_entries = []
+    for lo in range(0, len(all_entries), per):
+        part = all_entries[lo:lo + per]
+        d_off, d_size = add_block(part)
+        index_entries.append((part[-1][0], _put_varint(d_off) + _put_varint(d_size)))
     m_off, m_size = add_block([])
-    last_key = kv[-1][0] if kv else b""
-    i_off, i_size = add_block([(last_key, _put_varint(d_off) + _put_varint(d_size))])
+    i_off, i_size = add_block(index_entries)
     footer = _put_varint(m_off) + _put_varint(m_size) + _put_varint(i_off) + _put_varint(i_size)
     footer += b"\x00" * (40 - len(footer)) + struct.pack("<Q", MAGIC)
     with open(prefix + ".index", "wb") as fh:

@@ -83,3 +83,43 @@ def test_call_mods_cli_from_feature_file_and_from_reads(tmp_path):
         c = ln.split("\t")
         assert c[1] == str(feats[i][1]) and c[4] == feats[i][4] and c[3] == "-1"
         assert abs(float(c[6]) - q0[i]) <= 2e-4
+
+
+def test_call_mods_binary_records_path(tmp_path):
+    """the reference's 1628-byte binary sample records as a zero-parse call_mods input."""
+    from deepsignal_b200 import binary_format as bf
+    ck = W.random_checkpoint(17, "stress")
+    model_p = str(tmp_path / "m.ckpt.npz")
+    W.save_npz(model_p, ck)
+    f = synth_features(700, seed=43)
+    bin_p = str(tmp_path / "samples.bin")
+    bf.write_binary(bin_p, f["kmer"], f["means"], f["stds"], f["lens"], f["signals"], np.ones(700, np.int64))
+    res_p = str(tmp_path / "calls.tsv")
+    _run("call_mods", "-i", bin_p, "-m", model_p, "-o", res_p, "--precision", "fp16x2")
+    lines = open(res_p).read().splitlines()
+    assert len(lines) == 700
+    ref, ref_pred = mo.forward(ck, f["kmer"], f["means"], f["stds"], f["lens"], f["signals"])
+    p0n, p1n = mo.host_normalise(ref)
+    for i, ln in enumerate(lines):
+        c = ln.split("\t")
+        assert len(c) == 10 and c[:6] == ["."] * 6 and c[9] == "".join("ACGTN"[k] for k in f["kmer"][i])
+        assert abs(float(c[6]) - p0n[i]) <= 2e-3 and abs(float(c[7]) - p1n[i]) <= 2e-3
+
+
+def test_call_mods_devices_flag_matches_single_gpu(tmp_path):
+    """--devices shards the reads over several GPUs; the result file must be byte-identical to the 1-GPU run.
+    Needs two GPUs for the real thing; on one GPU the same device is used twice (two engines, two worker threads)."""
+    import torch
+    ck = W.random_checkpoint(17, "stress")
+    model_p = str(tmp_path / "m.ckpt.npz")
+    W.save_npz(model_p, ck)
+    rb = synth_reads(300, seed=44, nb_lo=300, nb_hi=700, cg_frac=0.03)
+    reads_p = str(tmp_path / "reads.npz")
+    save_reads(reads_p, rb)
+    one = str(tmp_path / "one.tsv")
+    _run("call_mods", "-i", reads_p, "-m", model_p, "-o", one, "--f5_batch_num", "1")
+    devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    two = str(tmp_path / "two.tsv")
+    _run("call_mods", "-i", reads_p, "-m", model_p, "-o", two, "--f5_batch_num", "1", "--devices", devs)
+    a, b = open(one).read(), open(two).read()
+    assert len(a.splitlines()) > 500 and a == b

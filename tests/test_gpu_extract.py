@@ -149,3 +149,105 @@ def test_wide_adc_range_uses_global_histogram(engine):
     got = engine.extract(rb, ["CG"])
     want = _oracle(rb, ["CG"])
     _compare(got, want)
+
+
+def test_cfg2_full_size_4000_reads(engine):
+    """BASELINE configs[1] at its stated size: 4,000 synthetic reads (~117 k CpG sites).  The NumPy oracle needs ~50 ms per
+    read, so it checks a random 300-read subset site for site; the whole batch is checked through size-independent
+    properties: the result of the 4,000-read call equals the concatenation of four 1,000-read calls (batch invariance),
+    integer features are consistent with the event table, and every window obeys the reference's three-branch rule."""
+    rb = synth_reads(4000, seed=20260102)
+    got = engine.extract(rb, ["CG"])
+    n = got["n_sites"]
+    assert n > 100000
+    # (a) batch invariance
+    off = 0
+    for lo in range(0, 4000, 1000):
+        part = engine.extract(rb.slice(lo, lo + 1000), ["CG"])
+        m = part["n_sites"]
+        sl = slice(off, off + m)
+        assert np.array_equal(part["site_read"] + lo, got["site_read"][sl])
+        for k in ("site_loc", "pos", "pos_in_strand", "kmer", "lens_i32", "window"):
+            assert np.array_equal(part[k], got[k][sl]), k
+        for k in ("means64", "stds64", "signals64"):
+            assert np.array_equal(part[k], got[k][sl], equal_nan=True), k
+        off += m
+    assert off == n
+    # (b) integer features against the event table
+    r, loc = got["site_read"].astype(np.int64), got["site_loc"].astype(np.int64)
+    base_idx = rb.ev_off[r][:, None] + loc[:, None] + np.arange(-8, 9)[None, :]
+    code = np.full(256, 255, np.int32)
+    for ch, c in CODE.items():
+        code[ord(ch)] = c
+    assert np.array_equal(got["kmer"], code[rb.ev_base[base_idx]])
+    assert np.all(got["kmer"][:, 8] == CODE["C"]) and np.all(got["kmer"][:, 9] == CODE["G"])
+    assert np.array_equal(got["lens_i32"], rb.ev_len[base_idx])          # synthetic events lie inside the raw signal
+    assert np.all(np.diff(got["site_read"]) >= 0)                       # ordered by read, then by location
+    same = np.diff(got["site_read"]) == 0
+    assert np.all(np.diff(got["site_loc"])[same] > 0)
+    # (c) the window rule (extract_features.py:154-190) on every site
+    tot = got["lens_i32"].sum(axis=1)
+    mid = got["lens_i32"][:, 8]
+    mode = np.where(tot < 360, 0, np.where(mid >= 360, 1, 2))
+    assert np.array_equal(got["window"][:, 0], mode)
+    assert np.all(got["window"][mode == 0, 2] == tot[mode == 0]) and np.all(got["window"][mode != 0, 2] == 360)
+    assert set(np.unique(mode).tolist()) == {0, 1, 2}
+    short = np.nonzero(mode == 0)[0][:2000]
+    for i in short[:200]:
+        assert np.all(got["signals64"][i, tot[i]:] == 0.0)
+    # (d) oracle on a random subset of reads
+    rng = np.random.default_rng(4)
+    pick = np.sort(rng.choice(4000, size=300, replace=False))
+    for i in pick[:300]:
+        want = fo.extract_read(rb.read_dict(int(i)), ["CG"], 0, CONTIGS)
+        rows = np.nonzero(got["site_read"] == i)[0]
+        assert len(rows) == len(want)
+        if not want:
+            continue
+        assert np.array_equal(got["pos"][rows], np.asarray([w[1] for w in want]))
+        assert np.array_equal(got["pos_in_strand"][rows], np.asarray([w[3] for w in want]))
+        assert np.array_equal(got["lens_i32"][rows], np.asarray([w[9] for w in want]))
+        assert np.array_equal(got["means64"][rows], np.asarray([w[7] for w in want]))
+        assert np.array_equal(got["stds64"][rows], np.asarray([w[8] for w in want]))
+        assert np.array_equal(got["signals64"][rows], np.asarray([w[10] for w in want]))
+
+
+def test_positions_filter_matches_reference_rule(engine):
+    """--positions (extract_features.py:262-263): only sites whose chrom||pos||strand key is listed survive."""
+    from deepsignal_b200.extract_features import extract_batch_arrays, key_sep
+    rb = synth_reads(30, seed=83, nb_lo=400, nb_hi=900, cg_frac=0.03)
+    everything = _oracle(rb, ["CG"])
+    keys = [key_sep.join([w[1], str(w[2]), w[3]]) for w in everything]
+    positions = set(keys[::3]) | {key_sep.join(["chrNope", "12", "+"])}
+    arr, info = extract_batch_arrays(engine, rb, ["CG"], 0, 17, 360, "mad", positions)
+    want = []
+    for i in range(rb.n_reads):
+        want += fo.extract_read(rb.read_dict(i), ["CG"], 0, CONTIGS, 17, 360, 1, positions)
+    assert 0 < len(want) < len(everything)
+    assert arr["n_sites"] == len(want) == len(info)
+    assert [x.split("\t")[:3] for x in info] == [[w[0], str(w[1]), w[2]] for w in want]
+    assert np.array_equal(arr["lens_i32"], np.asarray([w[9] for w in want]))
+    assert np.array_equal(arr["signals64"], np.asarray([w[10] for w in want]))
+
+
+def test_unusable_reads_are_dropped_and_counted(engine):
+    """A read whose normalisation is undefined — no raw samples, non-positive scaling, or MAD = 0 (constant signal, numpy
+    would print inf / nan features) — yields no features and counts as a failed read; its neighbours are unaffected."""
+    from deepsignal_b200.extract_features import _extract_features
+    rb = synth_reads(8, seed=84, nb_lo=300, nb_hi=500, cg_frac=0.04)
+    clean = _oracle(rb, ["CG"])
+    bad = synth_reads(8, seed=84, nb_lo=300, nb_hi=500, cg_frac=0.04)
+    bad.scaling = bad.scaling.copy()
+    bad.scaling[2] = 0.0                                   # non-physical scaling
+    raw = bad.raw.copy()
+    raw[bad.raw_off[5]:bad.raw_off[6]] = 480               # constant signal: MAD = 0
+    bad.raw = raw
+    feats, err = _extract_features(bad, None, None, "mad", ["CG"], 0, CONTIGS, 17, 360, 1, None, engine=engine)
+    assert err == 2
+    want = [w for w in clean if w[0] not in (2, 5)]
+    assert len(feats) == len(want) > 0
+    assert [f[1] for f in feats] == [w[2] for w in want]
+    assert all(np.array_equal(f[10], w[11]) for f, w in zip(feats, want))
+    got = engine.extract(bad, ["CG"])
+    assert not np.any(got["site_read"] == 2)                # the kernels emit nothing for a read without a LUT
+    assert not np.isfinite(got["read_scale"][2]) and got["read_scale"][5] == 0.0

@@ -355,3 +355,56 @@ def test_call_mods_two_rank_process_sharding_is_byte_identical(tmp_path, monkeyp
     out = str(tmp_path / "two.tsv")
     mp.spawn(_gloo_call_mods_worker, args=(2, port, tsv, out), nprocs=2, join=True)
     assert open(out).read() == one
+
+
+def _crc32c_bitwise(data):
+    """Second, table-free implementation of CRC-32C (Castagnoli, reflected polynomial 0x82F63B78)."""
+    crc = 0xFFFFFFFF
+    for b in data:
+        crc ^= b
+        for _ in range(8):
+            crc = (crc >> 1) ^ (0x82F63B78 & -(crc & 1))
+    return crc ^ 0xFFFFFFFF
+
+
+def test_tf_bundle_snappy_blocks_crc_and_prefix_compression(tmp_path):
+    """Index blocks as TF's table builder writes them: prefix-shared keys (restart interval 16), several data blocks,
+    Snappy-compressed (type 1) with a masked crc32c trailer.  The Snappy decoder is also fed hand-assembled streams."""
+    from deepsignal_b200 import tf_bundle, weights as W
+    # --- hand-assembled Snappy streams (format description: literal 00, copy-1 01, copy-2 10)
+    assert tf_bundle.snappy_decompress(bytes([5, 4 << 2]) + b"hello") == b"hello"
+    # "abcd" literal, then copy-1: len 4+((tag>>2)&7)=8, offset 4 -> overlapping repeat
+    assert tf_bundle.snappy_decompress(bytes([12, 3 << 2]) + b"abcd" + bytes([(4 << 2) | 1, 4])) == b"abcdabcdabcd"
+    # copy-2: tag = ((len-1)<<2)|2, offset LE16
+    assert tf_bundle.snappy_decompress(bytes([10, 4 << 2]) + b"01234" + bytes([(4 << 2) | 2, 5, 0])) == b"0123401234"
+    # long literal with a 1-byte length field (tag 60)
+    blob = bytes(range(200))
+    assert tf_bundle.snappy_decompress(tf_bundle._put_varint(200) + bytes([60 << 2, 199]) + blob) == blob
+    with pytest.raises(ValueError):
+        tf_bundle.snappy_decompress(bytes([4, (4 << 2) | 2, 9, 0]))         # copy before any output
+    rng = np.random.default_rng(0)
+    for payload in (b"", b"a", b"model/signalm/" * 300, bytes(rng.integers(0, 256, 5000, dtype=np.uint8)),
+                    (b"incp_layer" + bytes(rng.integers(0, 4, 3000, dtype=np.uint8))) * 3):
+        assert tf_bundle.snappy_decompress(tf_bundle.snappy_compress(payload)) == payload
+    # --- crc32c: table implementation vs the bitwise one
+    for payload in (b"", b"123456789", bytes(rng.integers(0, 256, 4097, dtype=np.uint8))):
+        assert tf_bundle.crc32c(payload) == _crc32c_bitwise(payload)
+    # --- compressed, multi-block bundle with the full variable list of the model (names share long prefixes)
+    ck = W.random_checkpoint(3, "tf_default")
+    small = {k: (v if v.size < 5000 else v.reshape(-1)[:64].copy()) for k, v in ck.items()}
+    prefix = str(tmp_path / "c.ckpt")
+    tf_bundle.write_bundle(prefix, small, compress=True, block_entries=37)
+    raw_prefix = str(tmp_path / "r.ckpt")
+    tf_bundle.write_bundle(raw_prefix, small, compress=False, block_entries=37)
+    assert os.path.getsize(prefix + ".index") < 0.6 * os.path.getsize(raw_prefix + ".index")   # the names compress well
+    for pfx in (prefix, raw_prefix):
+        back = tf_bundle.read_bundle(pfx)
+        assert set(back) == set(small)
+        for k, v in small.items():
+            assert np.array_equal(back[k], v), k
+    # a flipped payload bit is caught by the block crc
+    data = bytearray(open(prefix + ".index", "rb").read())
+    data[10] ^= 0x40
+    open(prefix + ".index", "wb").write(bytes(data))
+    with pytest.raises(ValueError, match="crc32c"):
+        tf_bundle.read_index(prefix)
