@@ -155,12 +155,12 @@ __global__ void pool3s1_kernel(const T* __restrict__ x, T* __restrict__ y, int64
   if (r > 0) {
     const Vec8<T> b = Vec8<T>::load(x + (r - 1) * ld + c);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a.v[i] = fmaxf(a.v[i], b.v[i]);
+    for (int i = 0; i < 8; ++i) a.v[i] = max_keep_nan(a.v[i], b.v[i]);
   }
   if (r + 1 < M) {
     const Vec8<T> b = Vec8<T>::load(x + (r + 1) * ld + c);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a.v[i] = fmaxf(a.v[i], b.v[i]);
+    for (int i = 0; i < 8; ++i) a.v[i] = max_keep_nan(a.v[i], b.v[i]);
   }
   a.store(y + r * ld + c);
 }
@@ -179,7 +179,8 @@ struct Pair8 {
   __device__ __forceinline__ void take_max(const Pair8& o) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const bool gt = o.h[i] > h[i] || (o.h[i] == h[i] && o.l[i] > l[i]);
+      // a NaN part wins as well: an overflowed activation must stay visible to the head kernel's non-finite check
+      const bool gt = o.h[i] > h[i] || (o.h[i] == h[i] && o.l[i] > l[i]) || o.h[i] != o.h[i] || o.l[i] != o.l[i];
       h[i] = gt ? o.h[i] : h[i];
       l[i] = gt ? o.l[i] : l[i];
     }
@@ -250,7 +251,7 @@ __global__ void pool3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int64
       if (q < 0 || q >= Lin) continue;
       const Vec8<T> b = Vec8<T>::load(x + (s * Lpin + q) * ld + c);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a.v[i] = fmaxf(a.v[i], b.v[i]);
+      for (int i = 0; i < 8; ++i) a.v[i] = max_keep_nan(a.v[i], b.v[i]);
     }
   }
   a.store(y + ro * ld + c);

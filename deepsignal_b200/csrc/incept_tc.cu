@@ -388,11 +388,17 @@ constexpr uint32_t B_ACC_STRIDE = 160;                 // columns: b3 [0,48) b4 
 
 // Split mode doubles every activation tile (hi + lo parts; the weights are shared), so it runs with two accumulator
 // stages and a 9-slot ring instead of three and ten.
+#ifndef DSB_B_SPLIT_SLOTS
+#define DSB_B_SPLIT_SLOTS 9
+#endif
+#ifndef DSB_B_SPLIT_ACC
+#define DSB_B_SPLIT_ACC 2
+#endif
 template <bool SPLIT>
 struct BSmemT {
   static constexpr int PARTS = SPLIT ? 2 : 1;
-  static constexpr int SLOTS = SPLIT ? 9 : 10;                // ring of plane tiles, 3 * PARTS per row tile
-  static constexpr int ACC_STAGES = SPLIT ? 2 : 3;
+  static constexpr int SLOTS = SPLIT ? DSB_B_SPLIT_SLOTS : 10;   // ring of plane tiles, 3 * PARTS per row tile
+  static constexpr int ACC_STAGES = SPLIT ? DSB_B_SPLIT_ACC : 3;
   static constexpr uint32_t w3 = 0;
   static constexpr uint32_t w4 = w3 + 3 * B_W48_BLK;
   static constexpr uint32_t w5b = w4 + 5 * B_W48_BLK;
@@ -405,6 +411,8 @@ struct BSmemT {
   static constexpr uint32_t nbars = 2 * SLOTS + 1 + 4 * ACC_STAGES;
   static constexpr uint32_t tmem_slot = (bars + 8 * nbars + 15u) & ~15u;
   static constexpr uint32_t total = tmem_slot + 16;
+  static_assert(total + 1024 <= 227 * 1024, "kernel B shared memory exceeds 227 KB");
+  static_assert(ACC_STAGES * B_ACC_STRIDE <= 512, "kernel B accumulator stages exceed TMEM");
 };
 
 template <bool F16, bool SPLIT>

@@ -59,6 +59,8 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 // ReLU that keeps NaN (fmaxf(NaN, 0) is 0): an overflowed 16-bit activation (inf, then inf - inf) must reach the head
 // kernel's non-finite check instead of being laundered into a finite wrong answer.
 __device__ __forceinline__ float relu_keep_nan(float v) { return v < 0.f ? 0.f : v; }
+// max that keeps NaN (fmaxf drops it): used by the pooling kernels for the same reason
+__device__ __forceinline__ float max_keep_nan(float a, float b) { return (b > a || b != b) ? b : a; }
 
 // exact-ish activations for the fp32 path, MUFU-based ones for the bf16 path
 template <bool FAST> __device__ __forceinline__ float act_tanh(float x) {

@@ -163,9 +163,43 @@ def run_call_mods(tsv_path, ckpt_path, out_path, nproc, torch_threads, batch_siz
     return time.perf_counter() - t0
 
 
+def run_call_mods_guarded(tsv_path, ckpt_path, out_path, nproc, torch_threads, timeout_s):
+    """`run_call_mods` in a fresh interpreter and its own process group, killed after ``timeout_s``.
+
+    The reference can deadlock with several caller processes: its Queue subclass (utils/process_utils.py:507-537)
+    decrements its shared size counter BEFORE the blocking get() and tests `empty()` as `counter == 0`, so two callers
+    that race for the last item drive the counter negative and one of them blocks in get() forever — call_mods then
+    never returns from `p.join()` (call_modifications.py:481-482).  A watchdog is therefore part of timing it.
+    Returns wall seconds, or None if the run had to be killed."""
+    import json
+    import signal
+    import subprocess
+    cmd = [sys.executable, "-m", "oracle.ref_host", tsv_path, ckpt_path, out_path, str(int(nproc)), str(int(torch_threads))]
+    proc = subprocess.Popen(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, start_new_session=True)
+    try:
+        out, _ = proc.communicate(timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        proc.wait()
+        return None
+    finally:
+        try:                        # daemonic children of a finished run are gone; make sure none survives a failed one
+            os.killpg(proc.pid, signal.SIGKILL)
+        except (ProcessLookupError, PermissionError):
+            pass
+    for line in reversed(out.strip().splitlines()):
+        if line.startswith("{"):
+            return float(json.loads(line)["seconds"])
+    return None
+
+
 def time_layouts(tsv_path, n_lines, ckpt_path, out_dir, cores=None, probe_only=None):
     """Both process layouts of SURVEY 8d: one caller with all threads (nproc=3 -> nproc_tf=1) and cores-2
-    single-thread callers (nproc=cores, call_modifications.py:461-476).  Returns {layout: samples/s}."""
+    single-thread callers (nproc=cores, call_modifications.py:461-476).  Returns {layout: samples/s}; a layout whose
+    run deadlocked (see run_call_mods_guarded) reports 0.0."""
     cores = cores or os.cpu_count() or 1
     res = {}
     layouts = {"1 caller x {} threads".format(cores): (3, cores),
@@ -173,6 +207,15 @@ def time_layouts(tsv_path, n_lines, ckpt_path, out_dir, cores=None, probe_only=N
     for name, (nproc, thr) in layouts.items():
         if probe_only and name not in probe_only:
             continue
-        dt = run_call_mods(tsv_path, ckpt_path, os.path.join(out_dir, "ref_calls.tsv"), nproc, thr)
-        res[name] = n_lines / dt
+        dt = run_call_mods_guarded(tsv_path, ckpt_path, os.path.join(out_dir, "ref_calls.tsv"), nproc, thr,
+                                   timeout_s=90.0 + n_lines / 150.0)
+        res[name] = (n_lines / dt) if dt else 0.0
     return res
+
+
+if __name__ == "__main__":
+    import json
+    _tsv, _ck, _out, _nproc, _thr = sys.argv[1:6]
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    print(json.dumps({"seconds": run_call_mods(_tsv, _ck, _out, int(_nproc), int(_thr))}))
