@@ -46,7 +46,8 @@ class Tensor(C.Structure):
 
 class PlanOptions(C.Structure):
     _fields_ = [("fused_blocks", C.c_int32), ("fused_front", C.c_int32), ("lstm_seq", C.c_int32),
-                ("ablate_a", C.c_int32), ("ablate_b", C.c_int32), ("ablate_gemm", C.c_int32), ("ablate_lstm", C.c_int32)]
+                ("ablate_a", C.c_int32), ("ablate_b", C.c_int32), ("ablate_gemm", C.c_int32), ("ablate_lstm", C.c_int32),
+                ("lstm_sms", C.c_int32)]
 
 
 class Reads(C.Structure):

@@ -179,7 +179,7 @@ struct dsb_ctx {
   dsb::FoldedModel model;
   dsb::Profiler prof;
   std::unique_ptr<dsb::ForwardPlan, dsb::PlanDeleter> plan[4];   // per precision
-  dsb_plan_options opts{1, 1, 1, 0, 0, 0, 0};
+  dsb_plan_options opts{1, 1, 1, 0, 0, 0, 0, 0};
   int* nonfinite_dev = nullptr;   // device counter written by the head kernel
   std::unique_ptr<dsb::ExtractWork, dsb::ExtractDeleter> xw;
   // staging for the _host entry points

@@ -207,30 +207,64 @@ __global__ void pool3s1_split_kernel(const __half* __restrict__ x, __half* __res
   a.store(y + r * ld + c, lo_out);
 }
 
-__global__ void pool3s2_split_kernel(const __half* __restrict__ x, __half* __restrict__ y, int64_t n, int C, int ld,
-                                     int Lin, int Lpin, int Lout, int Lpout, int pl, long long lo_in, long long lo_out) {
-  const int cv = C / 8;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * Lpout * cv) return;
-  const int c = (int)(idx % cv) * 8;
-  const int64_t ro = idx / cv;
-  const int64_t s = ro / Lpout;
-  const int po = (int)(ro % Lpout);
-  Pair8 a;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { a.h[i] = 0.f; a.l[i] = 0.f; }       // activations are >= 0 (post-ReLU)
-  if (po < Lout) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int q = 2 * po - pl + k;
-      if (q < 0 || q >= Lin) continue;
-      a.take_max(Pair8::load(x + (s * Lpin + q) * ld + c, lo_in));
-    }
+// ---- maxpool 1x3 stride 2 SAME between stages, 16-bit activations: one warp per output row, lanes over 16-byte channel
+// vectors (coalesced 480-byte row segments), packed half2 / bf162 maxima that keep NaN, 32-bit index math.  SPLIT: the
+// value is the pair (hi, lo); the winner has the largest hi and, among equal hi, the largest lo (see Pair8).
+template <bool F16> __device__ __forceinline__ uint32_t pmax_nan(uint32_t a, uint32_t b) {
+  if constexpr (F16) {
+    const __half2 r = __hmax2_nan(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __nv_bfloat162 r = __hmax2_nan(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
   }
-  a.store(y + ro * ld + c, lo_out);
+}
+// (ah, al) <- max((ah, al), (bh, bl)) elementwise on two packed fp16 pairs
+__device__ __forceinline__ void pair_max2(uint32_t& ah, uint32_t& al, uint32_t bh, uint32_t bl) {
+  const __half2 A = *reinterpret_cast<const __half2*>(&ah), B = *reinterpret_cast<const __half2*>(&bh);
+  const __half2 H = __hmax2_nan(A, B);
+  const uint32_t NEG = 0xfc00fc00u;                      // -inf, -inf
+  const uint32_t ma = __heq2_mask(A, H), mb = __heq2_mask(B, H);
+  const uint32_t la = (al & ma) | (NEG & ~ma), lb = (bl & mb) | (NEG & ~mb);
+  const __half2 L = __hmax2_nan(*reinterpret_cast<const __half2*>(&la), *reinterpret_cast<const __half2*>(&lb));
+  ah = *reinterpret_cast<const uint32_t*>(&H);
+  al = *reinterpret_cast<const uint32_t*>(&L);
 }
 
-// ---- maxpool 1x3 stride 2 SAME between stages (reference layers.py:211-213,224-226) ----------------
+template <bool SPLIT, bool F16>
+__global__ void __launch_bounds__(256) pool3s2_16_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int rows_out, int cv, int ld,
+                                                        int Lin, int Lpin, int Lout, int Lpout, int pl, long long lo_in, long long lo_out) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (int)(gridDim.x * (blockDim.x >> 5));
+  for (int row = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); row < rows_out; row += nwarps) {
+    const int s = row / Lpout, po = row - s * Lpout;
+    for (int c = lane; c < cv; c += 32) {
+      uint4 h = make_uint4(0u, 0u, 0u, 0u), l = make_uint4(0u, 0u, 0u, 0u);     // activations are >= 0 (post-ReLU): zero is neutral
+      if (po < Lout) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int q = 2 * po - pl + k;
+          if (q < 0 || q >= Lin) continue;
+          const uint16_t* src = x + ((size_t)s * Lpin + q) * ld + c * 8;
+          const uint4 vh = __ldg(reinterpret_cast<const uint4*>(src));
+          if constexpr (SPLIT) {
+            const uint4 vl = __ldg(reinterpret_cast<const uint4*>(src + lo_in));
+            pair_max2(h.x, l.x, vh.x, vl.x); pair_max2(h.y, l.y, vh.y, vl.y);
+            pair_max2(h.z, l.z, vh.z, vl.z); pair_max2(h.w, l.w, vh.w, vl.w);
+          } else {
+            h.x = pmax_nan<F16>(h.x, vh.x); h.y = pmax_nan<F16>(h.y, vh.y);
+            h.z = pmax_nan<F16>(h.z, vh.z); h.w = pmax_nan<F16>(h.w, vh.w);
+          }
+        }
+      }
+      uint16_t* dst = y + (size_t)row * ld + c * 8;
+      *reinterpret_cast<uint4*>(dst) = h;
+      if constexpr (SPLIT) *reinterpret_cast<uint4*>(dst + lo_out) = l;
+    }
+  }
+}
+
+// ---- maxpool 1x3 stride 2 SAME between stages (reference layers.py:211-213,224-226): generic / fp32 version -------
 template <class T>
 __global__ void pool3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, int C, int ld,
                                int Lin, int Lpin, int Lout, int Lpout, int pl) {

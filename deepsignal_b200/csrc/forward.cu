@@ -580,12 +580,17 @@ template <class T, bool SPLIT>
 void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, const float* means, const float* stds,
                const float* lens, const float* signals, float* probs, int32_t* pred, cudaStream_t main_stream) {
   const FoldedModel& fm = ctx->model;
+  constexpr bool TC16 = !std::is_same<T, float>::value;
   const bool multi = plan.multi_stream && !ctx->prof.enabled && fm.has_rnn() && fm.has_cnn();
   cudaStream_t streams[3] = {main_stream, multi ? plan.side[0] : main_stream, multi ? plan.side[1] : main_stream};
   // every persistent kernel sizes its grid to the whole GPU; the LSTM stream (L2 / tensor bound) and the CNN stream
   // (HBM bound) time-slice the SMs (partitioning them measured slower: profiles/r1_ablation.md)
-  const int sms[3] = {ctx->sm_count, ctx->sm_count, ctx->sm_count};
   const dsb_plan_options& opt = ctx->opts;
+  int sms[3] = {ctx->sm_count, ctx->sm_count, ctx->sm_count};
+  if (multi && opt.lstm_sms > 0 && opt.lstm_sms < ctx->sm_count) {       // SM budget per stream (dsb_plan_options.lstm_sms)
+    sms[1] = sms[2] = opt.lstm_sms & ~1;
+    sms[0] = ctx->sm_count - sms[1];
+  }
   bool forked = false;
   for (const Step& st : plan.steps) {
     cudaStream_t s = streams[st.stream];
@@ -668,12 +673,16 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_POOL2: {
         Timer tm(ctx, s, KC_ELEM, 0);
         const int64_t total = n * st.Lpout * (st.C / 8);
-        if constexpr (SPLIT)
-          pool3s2_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __half*>(st.src), reinterpret_cast<__half*>(st.dst), n, st.C, st.ld,
-                                                                               st.Lin, st.Lpin, st.Lout, st.Lpout, st.pl, st.lo_in, st.lo_out);
-        else
+        if constexpr (TC16) {
+          const int rows_out = (int)(n * st.Lpout);
+          const unsigned grid = (unsigned)std::min<int64_t>((rows_out + 7) / 8, (int64_t)ctx->sm_count * 16);
+          pool3s2_16_kernel<SPLIT, std::is_same<T, __half>::value><<<grid, 256, 0, s>>>(
+              reinterpret_cast<const uint16_t*>(st.src), reinterpret_cast<uint16_t*>(st.dst), rows_out, st.C / 8, st.ld,
+              st.Lin, st.Lpin, st.Lout, st.Lpout, st.pl, st.lo_in, st.lo_out);
+        } else {
           pool3s2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), n, st.C, st.ld,
                                                                             st.Lin, st.Lpin, st.Lout, st.Lpout, st.pl);
+        }
         DSB_CUDA(cudaGetLastError());
         ctx->launches++;
         break;

@@ -394,6 +394,9 @@ constexpr uint32_t B_ACC_STRIDE = 160;                 // columns: b3 [0,48) b4 
 #ifndef DSB_B_SPLIT_ACC
 #define DSB_B_SPLIT_ACC 2
 #endif
+#ifndef DSB_B_SPLIT_STG
+#define DSB_B_SPLIT_STG 2          // staging buffers per epilogue warp in split mode: 2 = hi and lo side by side, 1 = one after the other
+#endif
 template <bool SPLIT>
 struct BSmemT {
   static constexpr int PARTS = SPLIT ? 2 : 1;
@@ -405,8 +408,9 @@ struct BSmemT {
   static constexpr uint32_t w5c = w5b + 3 * B_W64_BLK;
   static constexpr uint32_t u = w5c + 2 * B_W48_BLK;          // 43008: per stage PARTS x two [128 x 32] blocks
   static constexpr uint32_t ring = u + 2 * PARTS * ACC_STAGES * B_U_BYTES;
-  static constexpr uint32_t stage = ring + SLOTS * B_SLOT_BYTES;            // 8 epilogue warps x 2 x 2 KB (TMA-store sources)
-  static constexpr uint32_t bars = stage + 16 * EPI_STAGE_BYTES;
+  static constexpr int STG = SPLIT ? DSB_B_SPLIT_STG : 2;                   // staging buffers per epilogue warp
+  static constexpr uint32_t stage = ring + SLOTS * B_SLOT_BYTES;            // 8 epilogue warps x STG x 2 KB (TMA-store sources)
+  static constexpr uint32_t bars = stage + 8 * STG * EPI_STAGE_BYTES;
   // barriers: full[S] empty[S] wbar b5b_full[A] u_full[A] tfull[A] tempty[A]
   static constexpr uint32_t nbars = 2 * SLOTS + 1 + 4 * ACC_STAGES;
   static constexpr uint32_t tmem_slot = (bars + 8 * nbars + 15u) & ~15u;
@@ -598,7 +602,7 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const __grid_constant_
     // Split mode: the hi tile goes through staging buffer 0, the lo tile through buffer 1.
     const int q = warp & 3;
     const int half = (warp - 6) >> 2;
-    const uint32_t stage = base + BSmem::stage + (uint32_t)(warp - 6) * 2u * EPI_STAGE_BYTES;
+    const uint32_t stage = base + BSmem::stage + (uint32_t)(warp - 6) * (uint32_t)BSmem::STG * EPI_STAGE_BYTES;
     uint32_t stage_sel = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -669,7 +673,25 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const __grid_constant_
           }
         }
         const uint32_t sw = (uint32_t)((lane >> 1) & 3);
-        if constexpr (SPLIT) {
+        if constexpr (SPLIT && BSmem::STG == 1) {
+          // one staging buffer: the hi tile and the lo tile go through it one after the other
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            const uint32_t (&pp)[16] = part == 0 ? pk : pl;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc)
+              sts128(stage + (uint32_t)lane * 64u + (((uint32_t)pc ^ sw) << 4), make_uint4(pp[4 * pc], pp[4 * pc + 1], pp[4 * pc + 2], pp[4 * pc + 3]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && !(p.ablate & 2)) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(part == 0 ? &maps.ys : &maps.ysl)), "r"(stage), "r"(96 + t0), "r"(wrow0) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        } else if constexpr (SPLIT) {
           // both staging buffers were the sources of the previous group's two stores
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();

@@ -108,6 +108,8 @@ typedef struct dsb_plan_options {
   int32_t fused_front;    /* 1: conv1 + pool + conv2 + conv3 in one kernel (single 16-bit modes); 0: stem + 2 GEMMs */
   int32_t lstm_seq;       /* 1: whole BiLSTM in one persistent kernel; 0: one GEMM launch per (dir, layer, step) */
   int32_t ablate_a, ablate_b, ablate_gemm, ablate_lstm;
+  int32_t lstm_sms;       /* 0: every kernel sizes its grid to the whole GPU (the streams time-slice the SMs);
+                             k > 0: the LSTM kernel runs on k SMs beside the CNN kernels on the other SMs          */
 } dsb_plan_options;
 DSB_API int dsb_get_plan_options(const dsb_ctx* ctx, dsb_plan_options* out);
 DSB_API int dsb_set_plan_options(dsb_ctx* ctx, const dsb_plan_options* opts);

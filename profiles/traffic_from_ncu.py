@@ -39,7 +39,9 @@ def main():
             k[m] = val * scale
     kern = OrderedDict()
     for (_, name), v in per.items():
-        kern.setdefault(name, []).append(v)
+        if "at::" in name:              # torch's own kernels (input generation of the driver script), not the library's
+            continue
+        kern.setdefault(name.replace("void ", "").replace("<unnamed>::", ""), []).append(v)
     out = {"source": src + " (ncu --clock-control none)", "chunk_samples": chunk, "kernels": OrderedDict()}
     total = 0.0
     for name, launches in kern.items():
