@@ -386,16 +386,19 @@ constexpr uint32_t B_W48_BLK = 48 * 32 * 2;            // 3072
 constexpr uint32_t B_W64_BLK = 64 * 32 * 2;            // 4096
 constexpr uint32_t B_ACC_STRIDE = 160;                 // columns: b3 [0,48) b4 [48,96) b5b [96,160), b5c re-uses [96,144)
 
-// Split mode doubles every activation tile (hi + lo parts; the weights are shared), so it runs with two accumulator
-// stages and a 9-slot ring instead of three and ten.
+// Split mode doubles every activation tile (hi + lo parts; the weights are shared): the U tiles take 96 KB for three
+// accumulator stages, which leaves an 8-slot ring and one staging buffer per epilogue warp.
+// Split-mode geometry of kernel B (build-time switches for A/B timing; profiles/r2_ablation.md): three accumulator stages
+// (so the tap GEMMs of tile i+2 do not wait for the epilogue of tile i), an 8-slot ring and one staging buffer per epilogue
+// warp measured 6.1 ms per 37,888-sample chunk against 6.9 ms for 2 stages / 9 slots / 2 buffers and 7.4 ms for 2 / 10 / 1.
 #ifndef DSB_B_SPLIT_SLOTS
-#define DSB_B_SPLIT_SLOTS 9
+#define DSB_B_SPLIT_SLOTS 8
 #endif
 #ifndef DSB_B_SPLIT_ACC
-#define DSB_B_SPLIT_ACC 2
+#define DSB_B_SPLIT_ACC 3
 #endif
 #ifndef DSB_B_SPLIT_STG
-#define DSB_B_SPLIT_STG 2          // staging buffers per epilogue warp in split mode: 2 = hi and lo side by side, 1 = one after the other
+#define DSB_B_SPLIT_STG 1          // staging buffers per epilogue warp in split mode: 2 = hi and lo side by side, 1 = one after the other
 #endif
 template <bool SPLIT>
 struct BSmemT {
