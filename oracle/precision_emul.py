@@ -28,6 +28,14 @@ ALL_SITES = ("w_front", "w_blk", "w_lstm", "a_front", "a_planes", "a_u", "a_y", 
 
 
 def make_q(kind: str):
+    """fp16 / bf16: one rounding.  fp16+lo8: hi = fp16(x) plus lo = e5m2(fp16(x - hi)) — the 24-bit activation format
+    (fp16 high part + the high byte of the fp16 low part) of the split-operand mode's HBM layout."""
+    if kind == "fp16+lo8":
+        def q(x):
+            hi = x.to(torch.float16).to(torch.float64)
+            lo = (x - hi).to(torch.float16).to(torch.float8_e5m2).to(torch.float64)
+            return hi + lo
+        return q
     dt = {"fp16": torch.float16, "bf16": torch.bfloat16}[kind]
 
     def q(x):
@@ -36,9 +44,10 @@ def make_q(kind: str):
 
 
 class Emul:
-    def __init__(self, ckpt: dict, kind: str = "fp16", sites=ALL_SITES, y_blocks=None, prefix="model"):
+    def __init__(self, ckpt: dict, kind: str = "fp16", sites=ALL_SITES, y_blocks=None, prefix="model", act_kind=None):
         self.ck = {k: torch.as_tensor(np.asarray(v), dtype=torch.float64) for k, v in ckpt.items()}
         self.q = make_q(kind)
+        self.q_act = make_q(act_kind) if act_kind else self.q      # rounding of the a_* (activation) sites
         self.sites = set(sites)
         self.y_blocks = y_blocks          # None = all blocks round (w_blk, a_planes, a_u, a_y); else only these block numbers
         self.cur_block = None
@@ -49,7 +58,7 @@ class Emul:
             return x
         if self.cur_block is not None and self.y_blocks is not None and self.cur_block not in self.y_blocks:
             return x
-        return self.q(x)
+        return self.q_act(x) if site.startswith("a_") else self.q(x)
 
     def folded_conv(self, conv, bn):
         ck = self.ck
