@@ -15,7 +15,9 @@ faster single-rounding modes).
 
 Sub-records on the same line: `extract` = configs[1] (4k synthetic reads through the extraction
 kernels: sites/s, achieved GB/s against SURVEY 8d's 2*N_raw + 9*n_bases + 1677*n_sites, per-kernel ms)
-and `e2e_reads` = configs[3] (extraction + forward, reads sharded over the ranks).
+and `e2e_reads` = configs[3] (extraction + forward, reads sharded over the ranks); at N=1 also `feature_file` =
+configs[0] through this implementation's CLI host path (100 k-line feature file in, result TSV out), the workload the
+`cpu_baseline` / `--impl reference` leg runs through the reference's own code.
 
 Reads / samples shard across GPUs with no collective (one process per GPU; torch.distributed is used
 only for the barrier and the max-over-ranks of the device time) -> "scaling": "weak".
@@ -315,6 +317,38 @@ def bench_reads(a, eng, torch, dev, rank, world, barrier, max_over_ranks):
     return res
 
 
+def bench_feature_file(a, n_lines=100000):
+    """configs[0] on this implementation: `deepsignal call_mods` (host path: C++ text codec -> dsb_forward_host -> C++ result
+    formatting) on an n_lines bn17/sn360 feature file, file in to file out, engine start-up included like the reference arm."""
+    from deepsignal_b200 import weights as W
+    from deepsignal_b200 import call_modifications as cm
+    from deepsignal_b200.synth import synth_features, write_feature_tsv, SEED_CFG1
+    import contextlib
+    with tempfile.TemporaryDirectory(prefix="dsb_cli_") as tmp:
+        ck = os.path.join(tmp, "stress_ckpt.npz")
+        W.save_npz(ck, W.random_checkpoint(17, "stress"))
+        tsv = os.path.join(tmp, "features.tsv")
+        t0 = time.perf_counter()
+        write_feature_tsv(tsv, synth_features(n_lines, seed=SEED_CFG1))
+        t_gen = time.perf_counter() - t0
+        out = os.path.join(tmp, "calls.tsv")
+        f5 = (True, "RawGenomeCorrected_000", "BaseCalled_template", None, True, "mad", "CG", 0, 1, 20, None)
+        best = None
+        for _ in range(2):          # second run: page cache warm, like the reference arm's repeated steps
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(sys.stderr):
+                cm.call_mods(tsv, ck, out, 17, 360, 512, 0.001, 2, os.cpu_count() or 1, True, True, True, True, f5,
+                             precision=a.precision, device=int(os.environ.get("LOCAL_RANK", "0")))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        n_out = sum(1 for _ in open(out))
+        size = os.path.getsize(tsv)
+    return {"workload": "BASELINE configs[0] on this implementation: deepsignal call_mods on a {}-line bn17/sn360 feature file ({} MB of "
+                        "text), file in -> file out, checkpoint load and plan build included".format(n_lines, size >> 20),
+            "samples_per_s": n_out / best, "seconds": best, "lines_out": n_out, "dtype": a.precision,
+            "feature_file_generation_s": t_gen}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,6 +365,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-reads", action="store_true", help="skip the extract / e2e_reads sub-records")
+    ap.add_argument("--no-cli", action="store_true", help="skip the feature_file sub-record (configs[0] through the CLI host path)")
     ap.add_argument("--parity-samples", type=int, default=100000)
     ap.add_argument("--reads", type=int, default=4000, help="synthetic reads per device-resident batch (configs[1])")
     ap.add_argument("--e2e-reads", type=int, default=128000, help="reads per GPU per e2e_reads step (configs[3]: 1 M reads at 8 GPUs)")
@@ -487,6 +522,8 @@ def main():
         out.update(bench_reads(a, eng, torch, dev, rank, world, barrier, max_over_ranks))
     if rank == 0 and not a.no_parity:
         out["parity"] = parity_block(eng, ckpt, a.precision, n=a.parity_samples)
+    if rank == 0 and world == 1 and not a.no_cli:
+        out["feature_file"] = bench_feature_file(a)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
         pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-probe", "--cpu-samples", str(a.cpu_samples)],

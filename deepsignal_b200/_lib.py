@@ -24,7 +24,7 @@ EXPORTS = [
     "dsb_set_max_chunk", "dsb_get_plan_options", "dsb_set_plan_options", "dsb_workspace_bytes", "dsb_forward_dev",
     "dsb_forward_host", "dsb_nonfinite_count",
     "dsb_set_profiling", "dsb_get_profile", "dsb_launch_count", "dsb_extract_dev",
-    "dsb_extract_host", "dsb_extract_max_sites", "dsb_extract_call_dev",
+    "dsb_extract_host", "dsb_extract_max_sites", "dsb_extract_call_dev", "dsb_site_frequency_host",
     "dsb_tsv_parse_features", "dsb_tsv_format_calls",
 ]
 
@@ -109,6 +109,7 @@ def load():
     lib.dsb_extract_max_sites.restype = i64
     lib.dsb_extract_call_dev.argtypes = [vp, i32, C.POINTER(Reads), C.POINTER(ExtractParams), C.POINTER(Sites),
                                          C.POINTER(i64), vp, vp, vp]
+    lib.dsb_site_frequency_host.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i64, C.POINTER(i64), vp, vp, vp, vp, vp]
     lib.dsb_tsv_parse_features.argtypes = [vp, i64, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), i32]
     lib.dsb_tsv_parse_features.restype = i64
     lib.dsb_tsv_format_calls.argtypes = [vp, vp, vp, i32, vp, vp, i64, vp, i64]

@@ -4,8 +4,10 @@
 Same inputs, options and output text as the reference's ``scripts/call_modification_frequency.py``
 (:17-79) with ``scripts/txt_formater.py`` (ModRecord / SiteStats / split_key): per (chromosome, position) key,
 sum of prob_0 / prob_1, counts of modified / unmodified calls, coverage, Rmet and the k-mer of the first record;
-``--bed`` writes bedMethyl.  Vectorised with NumPy (one pass, ``np.unique`` + ``np.add.at``) instead of a Python
-dict update per line; nothing here needs the GPU — the reduction is a few MB per million calls."""
+``--bed`` writes bedMethyl.  The reduction runs either on the host (NumPy: ``np.unique`` + ``np.add.at``, the default, no GPU
+needed) or, with ``--device N``, on the GPU as a segmented reduce keyed on (chromosome, position) through
+``dsb_site_frequency_host`` (csrc/sitefreq.cu: stable radix sort + one thread per site adding its records in line order);
+both give the reference's text byte for byte."""
 from __future__ import absolute_import
 
 import argparse
@@ -30,8 +32,9 @@ def _read_records(mods_files):
     return rows
 
 
-def calculate_mods_frequency(mods_files, prob_cf):
-    """Returns (keys, stats) with keys in first-appearance order like the reference's dict."""
+def calculate_mods_frequency(mods_files, prob_cf, device=None):
+    """Returns (keys, stats) with keys in first-appearance order like the reference's dict.
+    ``device``: CUDA device index -> aggregate on the GPU (libdsb200); None -> NumPy on the host."""
     rows = _read_records(mods_files)
     count = len(rows)
     if count == 0:
@@ -43,6 +46,21 @@ def calculate_mods_frequency(mods_files, prob_cf):
     p1 = np.asarray([float(r[7]) for r in rows], np.float64)
     lab = np.asarray([int(r[8]) for r in rows], np.int64)
     use = np.abs(p0 - p1) >= prob_cf                     # ModRecord.is_record_callable
+    if device is not None:
+        from .engine import Engine
+        names, chrom_id = np.unique(chrom, return_inverse=True)
+        eng = Engine(int(device))
+        try:
+            r = eng.site_frequency(chrom_id.astype(np.int32), pos, p0, p1, (lab == 1).astype(np.uint8), use.astype(np.uint8))
+        finally:
+            eng.close()
+        firsts = r["first"]
+        stats = dict(chrom=chrom[firsts], pos=pos[firsts], strand=np.asarray([rows[i][2] for i in firsts]),
+                     pos_in_strand=np.asarray([int(rows[i][3]) for i in firsts], np.int64), prob_0=r["prob_0"], prob_1=r["prob_1"],
+                     met=r["met"], unmet=r["coverage"] - r["met"], coverage=r["coverage"], kmer=np.asarray([rows[i][9] for i in firsts]))
+        used = int(use.sum())
+        print("{:.2f}% ({} of {}) calls used..".format(used / float(count) * 100, used, count))
+        return [key_sep.join([str(chrom[i]), str(int(pos[i]))]) for i in firsts], stats
     idx = np.flatnonzero(use)
     keys_all = np.char.add(np.char.add(chrom, key_sep), pos.astype(str))
     uk, first, inv = np.unique(keys_all[idx], return_index=True, return_inverse=True)
@@ -94,6 +112,7 @@ def main():
     parser.add_argument("--sort", action="store_true", default=False)
     parser.add_argument("--prob_cf", type=float, action="store", required=False, default=0.0)
     parser.add_argument("--file_uid", type=str, action="store", required=False, default=None)
+    parser.add_argument("--device", type=int, default=None, help="CUDA device index: aggregate on the GPU (default: host NumPy)")
     args = parser.parse_args()
     mods_files = []
     for ipath in args.input_path:
@@ -107,7 +126,7 @@ def main():
         else:
             raise ValueError()
     print("get {} input file(s)..".format(len(mods_files)))
-    _, stats = calculate_mods_frequency(mods_files, args.prob_cf)
+    _, stats = calculate_mods_frequency(mods_files, args.prob_cf, device=args.device)
     write_sitekey2stats(stats, args.result_file, args.sort, args.bed)
 
 

@@ -333,6 +333,15 @@ int dsb_extract_host(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params
   });
 }
 
+int dsb_site_frequency_host(dsb_ctx* ctx, int64_t n, const int32_t* chrom_id, const int64_t* pos, const double* p0, const double* p1,
+                            const uint8_t* label, const uint8_t* use, int64_t capacity, int64_t* n_sites, int64_t* first,
+                            double* sum_p0, double* sum_p1, int64_t* met, int64_t* coverage) {
+  if (!ctx) return DSB_ERR_INVALID;
+  return guarded(ctx, [&] {
+    dsb::site_frequency_host(ctx, n, chrom_id, pos, p0, p1, label, use, capacity, n_sites, first, sum_p0, sum_p1, met, coverage);
+  });
+}
+
 int dsb_extract_call_dev(dsb_ctx* ctx, int32_t precision, const dsb_reads* reads, const dsb_extract_params* params,
                          const dsb_sites* sites, int64_t* n_sites, float* probs, int32_t* pred, void* cuda_stream) {
   if (!ctx) return DSB_ERR_INVALID;

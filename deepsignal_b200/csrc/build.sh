@@ -8,7 +8,7 @@ NVCC=${NVCC:-nvcc}
 FLAGS="${EXTRA_NVCC:-} -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr"
 mkdir -p $BD
 pids=()
-for f in api fold gemm_f32 gemm_tc incept_tc lstm_seq2 front2_tc forward extract; do
+for f in api fold gemm_f32 gemm_tc incept_tc lstm_seq2 front2_tc forward extract sitefreq; do
   if [ ! -f $BD/$f.o ] || [ $f.cu -nt $BD/$f.o ] || [ -n "$(find . -maxdepth 1 -name '*.cuh' -newer $BD/$f.o)" ] || [ ../../include/dsb200.h -nt $BD/$f.o ]; then
     $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f.cu -o $BD/$f.o &
     pids+=($!)
@@ -19,5 +19,5 @@ if [ ! -f $BD/tsv.o ] || [ tsv.cpp -nt $BD/tsv.o ] || [ ../../include/dsb200.h -
   pids+=($!)
 fi
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $BD/api.o $BD/fold.o $BD/gemm_f32.o $BD/gemm_tc.o $BD/incept_tc.o $BD/lstm_seq2.o $BD/front2_tc.o $BD/forward.o $BD/extract.o $BD/tsv.o -cudart static
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $BD/api.o $BD/fold.o $BD/gemm_f32.o $BD/gemm_tc.o $BD/incept_tc.o $BD/lstm_seq2.o $BD/front2_tc.o $BD/forward.o $BD/extract.o $BD/sitefreq.o $BD/tsv.o -cudart static
 echo "built $(realpath $OUT)"

@@ -216,6 +216,10 @@ void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, co
                  const float* stds, const float* lens, const float* signals, float* probs, int32_t* pred,
                  cudaStream_t stream);
 size_t forward_workspace_bytes(const dsb_ctx* ctx, int64_t chunk, int precision);
+// sitefreq.cu
+void site_frequency_host(dsb_ctx* ctx, int64_t n, const int32_t* chrom, const int64_t* pos, const double* p0, const double* p1,
+                         const uint8_t* label, const uint8_t* use, int64_t capacity, int64_t* n_sites, int64_t* first,
+                         double* s0, double* s1, int64_t* met, int64_t* cov);
 // extract.cu
 void extract_dev(dsb_ctx* ctx, const dsb_reads* reads, const dsb_extract_params* params, const dsb_sites* sites,
                  int64_t* n_sites, double* read_shift, double* read_scale, cudaStream_t stream);

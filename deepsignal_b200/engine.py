@@ -160,6 +160,24 @@ class Engine(object):
     def launch_count(self) -> int:
         return int(self.lib.dsb_launch_count(self.h))
 
+    # ------------------------------------------------------------------ site frequencies
+    def site_frequency(self, chrom_id, pos, p0, p1, label, use):
+        """GPU segmented reduce over call_mods records keyed by (chrom_id, pos) (``dsb_site_frequency_host``).
+        Returns dict(first, prob_0, prob_1, met, coverage) in first-appearance order of the sites."""
+        n = len(pos)
+        chrom_id, pos = _np(chrom_id, np.int32, (n,)), _np(pos, np.int64, (n,))
+        p0, p1 = _np(p0, np.float64, (n,)), _np(p1, np.float64, (n,))
+        label, use = _np(label, np.uint8, (n,)), _np(use, np.uint8, (n,))
+        cap = max(1, n)
+        first, met, cov = np.empty(cap, np.int64), np.empty(cap, np.int64), np.empty(cap, np.int64)
+        s0, s1 = np.empty(cap, np.float64), np.empty(cap, np.float64)
+        ns = C.c_int64(0)
+        self._check(self.lib.dsb_site_frequency_host(self.h, n, _ptr(chrom_id), _ptr(pos), _ptr(p0), _ptr(p1), _ptr(label), _ptr(use),
+                                                     cap, C.byref(ns), _ptr(first), _ptr(s0), _ptr(s1), _ptr(met), _ptr(cov)))
+        k = int(ns.value)
+        order = np.argsort(first[:k], kind="stable")
+        return dict(first=first[:k][order], prob_0=s0[:k][order], prob_1=s1[:k][order], met=met[:k][order], coverage=cov[:k][order])
+
     # ------------------------------------------------------------------ extraction
     @staticmethod
     def _motif_bytes(motif_seqs):

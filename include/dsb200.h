@@ -209,6 +209,17 @@ DSB_API int dsb_extract_call_dev(dsb_ctx* ctx, int32_t precision, const dsb_read
                          const dsb_extract_params* params, const dsb_sites* sites, int64_t* n_sites,
                          float* probs, int32_t* pred, void* cuda_stream);
 
+/* ---- site-frequency aggregation of call_mods results -------------------------------
+ * Replaces the per-line dict update of the reference's scripts/call_modification_frequency.py:17-49 (ModRecord /
+ * SiteStats of scripts/txt_formater.py): records are keyed by (chrom id, pos); for every key among the records with
+ * use[i] != 0 it returns the index of the first record, the float64 sums of p0 / p1 accumulated in record order (bit-
+ * identical to the reference's +=), the number of records with label[i] != 0 and the coverage.  HOST pointers in and out;
+ * sites come in no particular order (sort by `first` for the reference's first-appearance order).  If more than
+ * `capacity` sites exist, *n_sites holds the count and DSB_ERR_CAPACITY is returned. */
+DSB_API int dsb_site_frequency_host(dsb_ctx* ctx, int64_t n, const int32_t* chrom_id, const int64_t* pos, const double* p0,
+                                    const double* p1, const uint8_t* label, const uint8_t* use, int64_t capacity,
+                                    int64_t* n_sites, int64_t* first, double* sum_p0, double* sum_p1, int64_t* met, int64_t* coverage);
+
 /* ---- text codec around the path (host only) ---------------------------------------
  * dsb_tsv_parse_features: parse whole lines of a 12-column feature file (reference
  * extract_features.py:289-303, reader call_modifications.py:35-91) from buf[0:len) into the model-input

@@ -123,3 +123,35 @@ def test_call_mods_devices_flag_matches_single_gpu(tmp_path):
     _run("call_mods", "-i", reads_p, "-m", model_p, "-o", two, "--f5_batch_num", "1", "--devices", devs)
     a, b = open(one).read(), open(two).read()
     assert len(a.splitlines()) > 500 and a == b
+
+
+def test_site_frequency_gpu_matches_reference_script(tmp_path):
+    """the (chrom, pos)-keyed aggregation as a GPU segmented reduce must reproduce the reference script's text
+    (golden produced by tests/golden/make_golden.py from scripts/call_modification_frequency.py) byte for byte, and agree
+    with the host NumPy path on a larger synthetic result file."""
+    import json
+    from deepsignal_b200 import call_modification_frequency as cmf
+    golden = os.path.join(ROOT, "tests", "golden")
+    ref = json.load(open(os.path.join(golden, "freq_ref.json")))
+    src = os.path.join(golden, "calls_small.tsv")
+    for tag, (cf, srt, bed) in dict(plain=(0.0, False, False), sort=(0.0, True, False), bed=(0.0, True, True), cf=(0.3, False, False)).items():
+        _, stats = cmf.calculate_mods_frequency([src], cf, device=0)
+        out = str(tmp_path / (tag + ".txt"))
+        cmf.write_sitekey2stats(stats, out, srt, bed)
+        assert open(out).read() == ref[tag], tag
+    # larger: 200k records over 3 contigs, ~20x coverage, both strands
+    rng = np.random.default_rng(9)
+    n = 200000
+    chrom = rng.choice(["chrA", "chrB", "chr10"], size=n)
+    pos = rng.integers(0, 3000, size=n)
+    p1 = rng.random(n).round(6)
+    big = str(tmp_path / "big.tsv")
+    with open(big, "w") as fh:
+        for i in range(n):
+            fh.write("\t".join([chrom[i], str(pos[i]), "+", str(pos[i]), "r%d" % (i % 977), "t", str(1.0 - p1[i]), str(p1[i]),
+                                str(int(p1[i] > 0.5)), "ACGTACGTCGACGTACG"]) + "\n")
+    for cf in (0.0, 0.4):
+        _, host = cmf.calculate_mods_frequency([big], cf)
+        _, dev = cmf.calculate_mods_frequency([big], cf, device=0)
+        for k in host:
+            assert np.array_equal(host[k], dev[k]), (cf, k)
