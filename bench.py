@@ -286,7 +286,7 @@ def bench_reads(a, eng, torch, dev, rank, world, barrier, max_over_ranks):
     eng.set_profiling(True)
     eng.extract_torch(dr, rb.n_reads, bufs)
     torch.cuda.synchronize(dev)
-    prof = {k: round(v["ms"], 4) for k, v in eng.profile().items() if k.startswith("x_")}
+    prof = {k: round(v["ms"], 4) for k, v in eng.profile().items() if k.startswith("x_") and v["launches"]}
     eng.set_profiling(False)
     ach = alg_bytes / (ms * 1e-3) / 1e9
     res["extract"] = {

@@ -31,7 +31,7 @@ EXPORTS = [
 
 # classes of dsb_get_profile (common.cuh KClass): forward kernels, then the extraction chain
 PROFILE_CLASSES = ("gemm", "lstm", "elementwise", "incept_a", "incept_b", "front",
-                   "x_read_norm", "x_sites", "x_lut", "x_base_stats", "x_site_feature")
+                   "x_read_norm", "x_sites", "x_lut", "x_unused", "x_site_feature")
 
 
 class DsbError(RuntimeError):

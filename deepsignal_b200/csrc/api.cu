@@ -260,6 +260,7 @@ int dsb_extract_host(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params
     DSB_CUDA(cudaSetDevice(ctx->device));
     ensure_streams(ctx);
     cudaStream_t s = ctx->stream_compute;
+    if (rd->raw_off[0] != 0 || rd->ev_off[0] != 0) dsb::fail(DSB_ERR_INVALID, "raw_off[0] and ev_off[0] must be 0");
     const int64_t total_raw = rd->raw_off[R], total_ev = rd->ev_off[R];
     for (int64_t i = 0; i < total_ev; ++i)
       if (rd->ev_start[i] < 0) dsb::fail(DSB_ERR_INVALID, "event %lld has a negative start (read_start_rel_to_raw + start < 0)", (long long)i);

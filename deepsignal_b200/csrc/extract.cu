@@ -7,11 +7,13 @@
 //                         for zscore.  Normalisation is elementwise in the raw value, so downstream
 //                         kernels recompute  around((scaling*(v+offset) - shift)/scale, 6)  from the int16
 //                         sample in float64 with IEEE-rounded primitives (bit-identical to numpy).
-//  2. base_stats_kernel   per base: clipped slice length, mean and population std in numpy's pairwise
-//                         summation order (float64).
+//  2. lut_kernel          per read: float64 table of the normalised value of every distinct int16 sample value.
 //  3. site_count / scan / site_emit   motif scan + ordered compaction of the targeted sites.
-//  4. site_feature_kernel per site (one warp): k-mer codes, 17 means/stds/lens, genome position and the
-//                         360-sample window rule (extract_features.py:154-190).
+//  4. site_feature_kernel per site (one warp): lanes 0..k-1 compute the clipped slice length, mean and population std
+//                         of their base in numpy's pairwise summation order (float64), then the warp writes the k-mer
+//                         codes, genome position and the 360-sample window (extract_features.py:154-190).  (Round 1
+//                         computed the base statistics in a separate per-base kernel over flagged bases: sparse warps,
+//                         0.49 ms of the 1.17 ms chain; per site they are dense and need no flag / per-base arrays.)
 #include <cmath>
 
 #include "common.cuh"
@@ -19,8 +21,8 @@
 namespace dsb {
 
 struct ExtractWork {
-  DevBuf base_mean, base_std, base_len, counts, offsets, shift, scale, scratch, total, tmp_read, tmp_loc;
-  DevBuf vmin, bins, lut_off, lut, need;
+  DevBuf counts, offsets, shift, scale, scratch, total, tmp_read, tmp_loc;
+  DevBuf vmin, bins, lut_off, lut;
 };
 void destroy_extract(ExtractWork* p) { delete p; }
 
@@ -265,20 +267,6 @@ template <class F> __device__ double pairwise_sum(const F& f, int a0, int n) {
   return ret;
 }
 
-__device__ __forceinline__ int find_read(const int64_t* off, int64_t R, int64_t e) {
-  int64_t a = 0, b = R;        // largest r with off[r] <= e
-  while (b - a > 1) { const int64_t m = (a + b) >> 1; if (off[m] <= e) a = m; else b = m; }
-  return (int)a;
-}
-
-struct BaseParams {
-  const int16_t* raw; const int64_t* raw_off;
-  const int32_t* ev_start; const int32_t* ev_len; const int64_t* ev_off; int64_t R; int64_t total_ev;
-  const double* lut; const int64_t* lut_off; const int32_t* vmin;
-  double* base_mean; double* base_std; int32_t* base_len;
-  const uint8_t* need;       // per base: 1 if some targeted site's k-mer covers it (others are never read downstream)
-};
-
 struct NormAt {
   const int16_t* x; const double* lut;       // lut already offset by -vmin
   __device__ double operator()(int i) const { return __ldg(lut + x[i]); }
@@ -287,38 +275,6 @@ struct SqDevAt {
   NormAt f; double mean;
   __device__ double operator()(int i) const { const double d = __dsub_rn(f(i), mean); return __dmul_rn(d, d); }
 };
-
-__global__ void base_stats_kernel(const BaseParams p) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= p.total_ev || !p.need[e]) return;
-  const int r = find_read(p.ev_off, p.R, e);
-  const int64_t N = p.raw_off[r + 1] - p.raw_off[r];
-  // python slice norm[s : s+l] for s >= 0 (negative starts are rejected on the host side)
-  int64_t s = p.ev_start[e], l = p.ev_len[e];
-  int64_t s0 = s < 0 ? 0 : (s > N ? N : s);
-  int64_t e0 = s + l;
-  e0 = e0 < s0 ? s0 : (e0 > N ? N : e0);
-  const int n = (int)(e0 - s0);
-  p.base_len[e] = n;
-  if (n == 0) { p.base_mean[e] = nan(""); p.base_std[e] = nan(""); return; }   // np.mean([]) -> nan
-  NormAt f{p.raw + p.raw_off[r] + s0, p.lut + p.lut_off[r] - p.vmin[r]};
-  const double mean = __ddiv_rn(pairwise_sum(f, 0, n), (double)n);
-  SqDevAt g{f, mean};
-  const double var = __ddiv_rn(pairwise_sum(g, 0, n), (double)n);
-  p.base_mean[e] = mean;
-  p.base_std[e] = sqrt(var);
-}
-
-// Only the bases inside some targeted site's k-mer are read by site_feature_kernel: flag them so that base_stats_kernel
-// skips the rest (CpG sites are ~1 % of the bases; whole warps of unflagged bases exit at once).
-__global__ void mark_need_kernel(const int32_t* __restrict__ site_read, const int32_t* __restrict__ site_loc, const int64_t* __restrict__ ev_off,
-                                 int64_t n_sites, int klen, uint8_t* __restrict__ need) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_sites * klen) return;
-  const int64_t sidx = i / klen;
-  const int k = (int)(i - sidx * klen);
-  need[ev_off[site_read[sidx]] + site_loc[sidx] - (klen - 1) / 2 + k] = 1;
-}
 
 struct MotifSet { int n, len, mod_loc, nbh; char seq[512]; };
 
@@ -426,7 +382,6 @@ __global__ void __launch_bounds__(128) site_emit_kernel(const uint8_t* ev_base, 
 struct SiteParams {
   dsb_reads rd;
   const double* lut; const int64_t* lut_off; const int32_t* vmin;
-  const double* base_mean; const double* base_std; const int32_t* base_len;
   const int32_t* site_read_in; const int32_t* site_loc_in;
   dsb_sites out;
   int64_t n_sites;
@@ -455,16 +410,27 @@ __global__ void __launch_bounds__(SITE_WARPS * 32) site_feature_kernel(const Sit
   int* cum = cum_s[w];
   int* st = st_s[w];
   // per-base gathers; K <= 33 -> up to two bases per lane
+  const double* lut = p.lut + p.lut_off[r] - p.vmin[r];
   for (int j = lane; j < K; j += 32) {
     const int64_t e = e0 + loc - nbh + j;
-    const int len = p.base_len[e];
-    int64_t s = p.rd.ev_start[e];
-    s = s < 0 ? 0 : (s > N ? N : s);
+    // python slice norm[s : s+l] for s >= 0 (negative starts are rejected on the host side), then np.mean / np.std of it
+    // in numpy's pairwise summation order (the sums are bit-identical to the reference's)
+    const int64_t s_raw = p.rd.ev_start[e], l_raw = p.rd.ev_len[e];
+    const int64_t s = s_raw < 0 ? 0 : (s_raw > N ? N : s_raw);
+    int64_t en = s_raw + l_raw;
+    en = en < s ? s : (en > N ? N : en);
+    const int len = (int)(en - s);
     st[j] = (int)s;
     cum[j + 1] = len;
     const int code = base_code(p.rd.ev_base[e]);
     if (p.out.kmer) p.out.kmer[site * K + j] = code;
-    const double mu = p.base_mean[e], sd = p.base_std[e];
+    double mu = nan(""), sd = nan("");                      // np.mean([]) -> nan
+    if (len > 0) {
+      NormAt f{x + s, lut};
+      mu = __ddiv_rn(pairwise_sum(f, 0, len), (double)len);
+      SqDevAt g{f, mu};
+      sd = sqrt(__ddiv_rn(pairwise_sum(g, 0, len), (double)len));
+    }
     if (p.out.means) p.out.means[site * K + j] = (float)mu;
     if (p.out.stds) p.out.stds[site * K + j] = (float)sd;
     if (p.out.lens) p.out.lens[site * K + j] = (float)len;
@@ -504,7 +470,6 @@ __global__ void __launch_bounds__(SITE_WARPS * 32) site_feature_kernel(const Sit
   if (lane == 0 && p.out.window) {
     p.out.window[site * 3] = mode; p.out.window[site * 3 + 1] = start; p.out.window[site * 3 + 2] = nreal;
   }
-  const double* lut = p.lut + p.lut_off[r] - p.vmin[r];
   for (int j = lane; j < S; j += 32) {
     double v = 0.0;
     if (j < nreal) {
@@ -535,20 +500,11 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
   DSB_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->xw) ctx->xw.reset(new ExtractWork());
   ExtractWork& w = *ctx->xw;
-  // event count: last element of ev_off (device) -> need it on the host
-  int64_t ends[2];
-  DSB_CUDA(cudaMemcpyAsync(&ends[0], rd->ev_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  DSB_CUDA(cudaMemcpyAsync(&ends[1], rd->ev_off, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  DSB_CUDA(cudaStreamSynchronize(s));
-  const int64_t total_ev = ends[0];
-  if (ends[1] != 0) fail(DSB_ERR_INVALID, "ev_off[0] must be 0");
+  // (raw_off[0] == ev_off[0] == 0 is part of the contract; dsb_extract_host checks it on its host arrays)
   const int grid_norm = (int)std::min<int64_t>(R, (int64_t)ctx->sm_count * 4);
   w.shift.ensure(R * sizeof(double));
   w.scale.ensure(R * sizeof(double));
   w.scratch.ensure((size_t)grid_norm * 65536 * sizeof(uint32_t));
-  w.base_mean.ensure(std::max<int64_t>(total_ev, 1) * sizeof(double));
-  w.base_std.ensure(std::max<int64_t>(total_ev, 1) * sizeof(double));
-  w.base_len.ensure(std::max<int64_t>(total_ev, 1) * sizeof(int32_t));
   w.counts.ensure(R * sizeof(int64_t));
   w.offsets.ensure((R + 1) * sizeof(int64_t));
 
@@ -610,29 +566,9 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
       site_emit_kernel<<<grid_r, 128, 0, s>>>(rd->ev_base, rd->ev_off, R, rd->raw_off, rd->scaling, ms, w.offsets.as<int64_t>(), emit, sr, sl);
     }
     DSB_CUDA(cudaGetLastError());
-    if (total_ev > 0) {
-      w.need.ensure((size_t)total_ev);
-      DSB_CUDA(cudaMemsetAsync(w.need.p, 0, (size_t)total_ev, s));
-      const int64_t marks = emit * prm->kmer_len;
-      {
-        Timer tm(ctx, s, KC_X_SITES, 0);
-        mark_need_kernel<<<(unsigned)((marks + 255) / 256), 256, 0, s>>>(sr, sl, rd->ev_off, emit, prm->kmer_len, w.need.as<uint8_t>());
-      }
-      DSB_CUDA(cudaGetLastError());
-      BaseParams bp{rd->raw, rd->raw_off, rd->ev_start, rd->ev_len, rd->ev_off, R, total_ev,
-                    w.lut.as<double>(), w.lut_off.as<int64_t>(), w.vmin.as<int32_t>(),
-                    w.base_mean.as<double>(), w.base_std.as<double>(), w.base_len.as<int32_t>(), w.need.as<uint8_t>()};
-      {
-        Timer tm(ctx, s, KC_X_BASE, 0);
-        base_stats_kernel<<<(unsigned)((total_ev + 127) / 128), 128, 0, s>>>(bp);
-      }
-      DSB_CUDA(cudaGetLastError());
-      ctx->launches += 2;
-    }
     SiteParams sp;
     sp.rd = *rd;
     sp.lut = w.lut.as<double>(); sp.lut_off = w.lut_off.as<int64_t>(); sp.vmin = w.vmin.as<int32_t>();
-    sp.base_mean = w.base_mean.as<double>(); sp.base_std = w.base_std.as<double>(); sp.base_len = w.base_len.as<int32_t>();
     sp.site_read_in = sr; sp.site_loc_in = sl;
     sp.out = *sites;
     sp.n_sites = emit;
@@ -642,7 +578,7 @@ void extract_dev(dsb_ctx* ctx, const dsb_reads* rd, const dsb_extract_params* pr
       site_feature_kernel<<<(unsigned)((emit + SITE_WARPS - 1) / SITE_WARPS), SITE_WARPS * 32, 0, s>>>(sp);
     }
     DSB_CUDA(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 2;      // site_emit + site_feature
   }
   if (total > sites->capacity) fail(DSB_ERR_CAPACITY, "%lld sites found but the output capacity is %lld", (long long)total, (long long)sites->capacity);
 }

@@ -139,7 +139,7 @@ DSB_API int dsb_nonfinite_count(dsb_ctx* ctx, int64_t* count);
  * stream around every launch of the class; the forward runs single-stream while profiling).  Classes:
  * 0 generic tensor-core / fp32 GEMM launches, 1 LSTM kernel(s), 2 elementwise helpers (pools, feature rows, head),
  * 3 inception kernel A, 4 inception kernel B, 5 fused front end (conv1..conv3);
- * extraction chain: 6 read_norm, 7 site count / scan / emit / mark, 8 LUT, 9 base_stats, 10 site_feature. */
+ * extraction chain: 6 read_norm, 7 site count / scan / emit, 8 LUT, 9 unused, 10 site_feature (incl. the per-base statistics). */
 DSB_API int dsb_set_profiling(dsb_ctx* ctx, int32_t enabled);
 DSB_API int dsb_get_profile(dsb_ctx* ctx, int32_t cls, double* ms_total, int64_t* launches, double* flops);
 DSB_API int64_t dsb_launch_count(const dsb_ctx* ctx);   /* kernels launched by this ctx so far */
@@ -148,13 +148,13 @@ DSB_API int64_t dsb_launch_count(const dsb_ctx* ctx);   /* kernels launched by t
 typedef struct dsb_reads {
   int64_t n_reads;
   const int16_t* raw;          /* [raw_off[n_reads]] concatenated Raw/Reads/ * /Signal         */
-  const int64_t* raw_off;      /* [n_reads+1]                                                  */
+  const int64_t* raw_off;      /* [n_reads+1], raw_off[0] == 0                                 */
   const double* scaling;       /* [n_reads] range / digitisation (extract_features.py:198-201) */
   const double* offset;        /* [n_reads] channel offset                                     */
   const int32_t* ev_start;     /* [ev_off[n_reads]] Events.start + read_start_rel_to_raw        */
   const int32_t* ev_len;       /* Events.length                                                */
   const uint8_t* ev_base;      /* Events.base (ASCII)                                          */
-  const int64_t* ev_off;       /* [n_reads+1]                                                  */
+  const int64_t* ev_off;       /* [n_reads+1], ev_off[0] == 0                                  */
   const int64_t* chrom_start;  /* [n_reads] Alignment.mapped_start                             */
   const uint8_t* strand_minus; /* [n_reads] 1 if Alignment.mapped_strand == '-'                */
   const int64_t* chrom_len;    /* [n_reads] contig length, -1 without --reference_path         */
