@@ -168,6 +168,15 @@ def _process_work(engine, model, work, ctx):
         arr, info = extract_batch_arrays(engine, work.payload, ctx["motif_seqs"], ctx["mod_loc"], ctx["kmer_len"],
                                          ctx["cent_signals_len"], ctx["normalize_method"], ctx["positions"], want64=False)
         errors = int(np.sum(failed_reads(arr)))
+        if len(info) == 0:
+            return [], 0, errors
+        if os.environ.get("DSB_PY_TSV", "0") != "1":
+            # forward + the C++ result formatter (byte-identical to the Python formatting of _call_mods, ~5 us per site faster)
+            from .fast_tsv import block_from_info, format_calls
+            probs, prediction = engine.forward(arr["kmer"], arr["means"], arr["stds"], arr["lens"], arr["signals"],
+                                               precision=model.precision)
+            text = format_calls(block_from_info(info, arr["kmer"]), probs, prediction).decode().rstrip("\n")
+            return [text], -(-len(info) // ctx["batch_size"]), errors
         batch = (info, arr["kmer"], arr["means"], arr["stds"], arr["lens"], arr["signals"], [ctx["methy_label"]] * len(info))
         pred_str, _, nb = _call_mods(batch, engine, model, ctx["learning_rate"], ctx["batch_size"])
         return pred_str, nb, errors

@@ -72,6 +72,24 @@ def iter_feature_blocks(path, kmer_len=17, signal_len=360, max_samples=None, nth
                 return
 
 
+def block_from_info(info_strings, kmer) -> FeatureBlock:
+    """A block for :func:`format_calls` from in-memory samples: ``info_strings`` = the six tab-joined info columns per
+    sample (what the reference calls ``sampleinfo``), ``kmer`` int32 [n, k] base codes (all must be 0..4)."""
+    kmer = np.ascontiguousarray(kmer, np.int32)
+    if kmer.size and (kmer.min() < 0 or kmer.max() > 4):
+        raise KeyError("base outside ACGTN in a k-mer")          # the reference's code2base_dna lookup raises KeyError here
+    enc = [s.encode() for s in info_strings]
+    lens = np.fromiter((len(e) for e in enc), dtype=np.int64, count=len(enc))
+    ends = np.cumsum(lens)
+    b = FeatureBlock()
+    b.n, b.kmer = len(enc), kmer
+    b.text = b"".join(enc) + b"\0"
+    b.text_ptr = C.cast(C.c_char_p(b.text), C.c_void_p).value
+    b.info_off = np.stack([ends - lens, ends], axis=1).astype(np.int64)
+    b.means = b.stds = b.lens = b.signals = b.labels = None
+    return b
+
+
 def format_calls(block, probs, pred) -> bytes:
     lib = _lib.load()
     n = block.n

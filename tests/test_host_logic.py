@@ -408,3 +408,24 @@ def test_tf_bundle_snappy_blocks_crc_and_prefix_compression(tmp_path):
     open(prefix + ".index", "wb").write(bytes(data))
     with pytest.raises(ValueError, match="crc32c"):
         tf_bundle.read_index(prefix)
+
+
+def test_block_from_info_formats_like_call_mods():
+    """The reads path of call_mods formats its result lines with the C++ codec from in-memory samples: same bytes as the
+    Python formatting of _call_mods (reference call_modifications.py:183-190)."""
+    from deepsignal_b200.fast_tsv import block_from_info, format_calls
+    rng = np.random.default_rng(3)
+    n = 500
+    info = ["chr%d\t%d\t%s\t%d\tread_%d\tt" % (i % 3, 1000 + i, "+-"[i % 2], -1 if i % 5 else 7 * i, i // 9) for i in range(n)]
+    kmer = rng.integers(0, 5, (n, 17)).astype(np.int32)
+    eng = _StubEngine(0)
+    z = [rng.random((n, 17), dtype=np.float32) for _ in range(3)]
+    sig = rng.random((n, 360), dtype=np.float32)
+    probs, pred = eng.forward(kmer, z[0], z[1], z[2], sig)
+    got = format_calls(block_from_info(info, kmer), probs, pred).decode().splitlines()
+    want, _, _ = cm._call_mods((info, kmer, z[0], z[1], z[2], sig, [1] * n), eng, cm._ModelHandle(17, 360, 2), 0.001, 512)
+    assert got == want
+    bad = kmer.copy()
+    bad[3, 4] = 255
+    with pytest.raises(KeyError):
+        block_from_info(info, bad)
