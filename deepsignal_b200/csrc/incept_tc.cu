@@ -400,22 +400,26 @@ constexpr uint32_t B_ACC_STRIDE = 160;                 // columns: b3 [0,48) b4 
 #ifndef DSB_B_SPLIT_STG
 #define DSB_B_SPLIT_STG 1          // staging buffers per epilogue warp in split mode: 2 = hi and lo side by side, 1 = one after the other
 #endif
+#ifndef DSB_B_SPLIT_USTG
+#define DSB_B_SPLIT_USTG 3         // U tiles (hi + lo, 32 KB each) in split mode; a U tile is free once its b5c MMAs have completed
+#endif
 template <bool SPLIT>
 struct BSmemT {
   static constexpr int PARTS = SPLIT ? 2 : 1;
   static constexpr int SLOTS = SPLIT ? DSB_B_SPLIT_SLOTS : 10;   // ring of plane tiles, 3 * PARTS per row tile
   static constexpr int ACC_STAGES = SPLIT ? DSB_B_SPLIT_ACC : 3;
+  static constexpr int U_STAGES = SPLIT ? DSB_B_SPLIT_USTG : 3;
   static constexpr uint32_t w3 = 0;
   static constexpr uint32_t w4 = w3 + 3 * B_W48_BLK;
   static constexpr uint32_t w5b = w4 + 5 * B_W48_BLK;
   static constexpr uint32_t w5c = w5b + 3 * B_W64_BLK;
   static constexpr uint32_t u = w5c + 2 * B_W48_BLK;          // 43008: per stage PARTS x two [128 x 32] blocks
-  static constexpr uint32_t ring = u + 2 * PARTS * ACC_STAGES * B_U_BYTES;
+  static constexpr uint32_t ring = u + 2 * PARTS * U_STAGES * B_U_BYTES;
   static constexpr int STG = SPLIT ? DSB_B_SPLIT_STG : 2;                   // staging buffers per epilogue warp
   static constexpr uint32_t stage = ring + SLOTS * B_SLOT_BYTES;            // 8 epilogue warps x STG x 2 KB (TMA-store sources)
   static constexpr uint32_t bars = stage + 8 * STG * EPI_STAGE_BYTES;
-  // barriers: full[S] empty[S] wbar b5b_full[A] u_full[A] tfull[A] tempty[A]
-  static constexpr uint32_t nbars = 2 * SLOTS + 1 + 4 * ACC_STAGES;
+  // barriers: full[S] empty[S] wbar b5b_full[A] u_full[A] tfull[A] tempty[A] u_empty[U]   (u_full indexed by U stage)
+  static constexpr uint32_t nbars = 2 * SLOTS + 1 + 4 * ACC_STAGES + U_STAGES;
   static constexpr uint32_t tmem_slot = (bars + 8 * nbars + 15u) & ~15u;
   static constexpr uint32_t total = tmem_slot + 16;
   static_assert(total + 1024 <= 227 * 1024, "kernel B shared memory exceeds 227 KB");
@@ -426,7 +430,8 @@ template <bool F16, bool SPLIT>
 __global__ void __launch_bounds__(B_THREADS, 1)
 incept_b_kernel(const __grid_constant__ InceptBMaps maps, const __grid_constant__ InceptBParams p, const int num_tiles) {
   using BSmem = BSmemT<SPLIT>;
-  constexpr int PARTS = BSmem::PARTS, B_SLOTS = BSmem::SLOTS, B_ACC_STAGES = BSmem::ACC_STAGES;
+  constexpr int PARTS = BSmem::PARTS, B_SLOTS = BSmem::SLOTS, B_ACC_STAGES = BSmem::ACC_STAGES, U_STAGES = BSmem::U_STAGES;
+  static_assert(U_STAGES <= B_ACC_STAGES, "at most one U tile per accumulator stage");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -437,6 +442,7 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const __grid_constant_
   auto u_full = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + B_ACC_STAGES + a); };
   auto tfull = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + 2 * B_ACC_STAGES + a); };
   auto tempty = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + 3 * B_ACC_STAGES + a); };
+  auto u_empty = [&](int a) { return base + BSmem::bars + 8u * (2 * B_SLOTS + 1 + 4 * B_ACC_STAGES + a); };
   const uint32_t tmem_slot = base + BSmem::tmem_slot;
   // U tile of accumulator stage a, part (0 hi / 1 lo), k-block kb
   auto u_blk = [&](int a, int part, int kb) { return base + BSmem::u + (uint32_t)((a * PARTS + part) * 2 + kb) * B_U_BYTES; };
@@ -445,6 +451,7 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const __grid_constant_
     for (int s = 0; s < B_SLOTS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     mbar_init(wbar, 1);
     for (int a = 0; a < B_ACC_STAGES; ++a) { mbar_init(b5b_full(a), 1); mbar_init(u_full(a), 4); mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
+    for (int a = 0; a < U_STAGES; ++a) mbar_init(u_empty(a), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -524,25 +531,27 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const __grid_constant_
       };
       // software pipeline across tiles: the tap GEMMs of tile i+1 are issued before waiting for the staged
       // relu(b5b) tile of tile i, so the TMEM -> smem round trip of branch 5 is off the critical path.
-      int acc = 0;
+      int acc = 0, k = 0;
       uint32_t acc_phase = 0;
       if ((int)blockIdx.x < num_tiles) front(0, 0);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
         const int nacc = (acc + 1 == B_ACC_STAGES) ? 0 : acc + 1;
         const uint32_t nphase = (nacc == 0) ? (acc_phase ^ 1u) : acc_phase;
         if (tile + (int)gridDim.x < num_tiles) front(nacc, nphase);
         const uint32_t d0 = tmem_base + acc * B_ACC_STRIDE;
-        mbar_wait(u_full(acc), acc_phase);                // relu(b5b) tile of this stage is in shared memory
+        const int ub = k % U_STAGES;                      // U tile of this CTA's k-th row tile
+        mbar_wait(u_full(ub), (uint32_t)(k / U_STAGES) & 1u);   // relu(b5b) tile is in shared memory
         tc_fence_after();
 #pragma unroll
         for (int part = 0; part < PARTS; ++part) {
           for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t ad = make_kmajor_desc<32>(u_blk(acc, part, kb));
+            const uint64_t ad = make_kmajor_desc<32>(u_blk(ub, part, kb));
             const uint64_t bd = make_kmajor_desc<32>(base + BSmem::w5c + kb * B_W48_BLK);
 #pragma unroll
             for (int k = 0; k < 2; ++k) tc_mma_bf16(d0 + 96, ad + 2 * k, bd + 2 * k, id48, (part | kb | k) != 0 ? 1u : 0u);
           }
         }
+        tc_commit(u_empty(ub));                           // the U tile may be rewritten once these MMAs have read it
         tc_commit(tfull(acc));
         acc = nacc;
         acc_phase = nphase;
@@ -551,25 +560,27 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const __grid_constant_
   } else if (warp < 6) {
     // ---------------- branch-5 staging warps: relu(b5b + bias) -> 16-bit A operand of the 1x1 that follows ----------------
     const int q = warp & 3;
-    int acc = 0;
+    int acc = 0, k = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
       const int i = q * 32 + lane;
       const int row = tile * 128 + i;
       const bool zero = row >= p.M || (row % p.Lp) >= p.L;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * B_ACC_STRIDE + 96u;
+      const int ub = k % U_STAGES;
       mbar_wait(b5b_full(acc), acc_phase);
       tc_fence_after();
       uint32_t rr[4][16];
 #pragma unroll
       for (int g = 0; g < 4; ++g) tc_ld16(t_row + 16u * g, rr[g]);
       tc_wait_ld();
+      mbar_wait(u_empty(ub), ((uint32_t)(k / U_STAGES) & 1u) ^ 1u);     // the b5c MMAs that read this U tile have completed
       const uint32_t sw = (uint32_t)((i >> 1) & 3);
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
         // k-block kb of U: row i is 64 bytes; logical 16-byte chunk c sits at c ^ ((i >> 1) & 3)  (SWIZZLE_64B)
-        const uint32_t ub = u_blk(acc, 0, kb) + (uint32_t)i * 64u;
-        const uint32_t ubl = u_blk(acc, PARTS - 1, kb) + (uint32_t)i * 64u;
+        const uint32_t ubh = u_blk(ub, 0, kb) + (uint32_t)i * 64u;
+        const uint32_t ubl = u_blk(ub, PARTS - 1, kb) + (uint32_t)i * 64u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[4], pl[4];
@@ -585,14 +596,14 @@ incept_b_kernel(const __grid_constant__ InceptBMaps maps, const __grid_constant_
             pk[k] = pack16<F16>(a, b);
             if constexpr (SPLIT) pl[k] = pack_lo(a, b, pk[k]);
           }
-          sts128(ub + (((uint32_t)c ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          sts128(ubh + (((uint32_t)c ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
           if constexpr (SPLIT) sts128(ubl + (((uint32_t)c ^ sw) << 4), make_uint4(pl[0], pl[1], pl[2], pl[3]));
         }
       }
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(u_full(acc));
+      if (lane == 0) mbar_arrive(u_full(ub));
       if (++acc == B_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
