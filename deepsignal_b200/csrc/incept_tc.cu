@@ -297,6 +297,7 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const __grid_constant_
       // 1x1 conv of x and is valid on all 128 tile rows (the rows shared with the neighbouring tile get identical values),
       // so those groups leave as one TMA store per warp: no shared-memory read-back by the threads.
       for (int g = half; g < 8; g += 2) {
+        if (p.ablate & 4) break;                           // timing experiment: the epilogue only releases the accumulator
         const int c = g < 7 ? g * 32 : 208;
         uint32_t rr[2][16];
         __syncwarp();

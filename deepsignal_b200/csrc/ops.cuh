@@ -58,7 +58,11 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 
 // ReLU that keeps NaN (fmaxf(NaN, 0) is 0): an overflowed 16-bit activation (inf, then inf - inf) must reach the head
 // kernel's non-finite check instead of being laundered into a finite wrong answer.
-__device__ __forceinline__ float relu_keep_nan(float v) { return v < 0.f ? 0.f : v; }
+__device__ __forceinline__ float relu_keep_nan(float v) {
+  float r;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));      // one FMNMX.NAN instead of a compare + select
+  return r;
+}
 // max that keeps NaN (fmaxf drops it): used by the pooling kernels for the same reason
 __device__ __forceinline__ float max_keep_nan(float a, float b) { return (b > a || b != b) ? b : a; }
 
