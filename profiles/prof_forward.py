@@ -55,7 +55,7 @@ def main():
     torch.cuda.synchronize()
     prof = eng.profile()
     eng.set_profiling(False)
-    out = {"precision": a.precision, "chunk": a.chunk, "ms_per_chunk": best / a.chunks, "samples_per_s": n / best * 1e3, "opts": opts}
+    out = {"precision": a.precision, "chunk": a.chunk, "ms_per_chunk": best / a.chunks, "samples_per_s": n / best * 1e3, "opts": opts, "lib": os.path.basename(os.environ.get("DSB_LIB", "libdsb200.so"))}
     for k, v in prof.items():
         if v["launches"]:
             out[k + "_ms_per_chunk"] = round(v["ms"] / a.chunks, 4)
