@@ -254,9 +254,8 @@ struct Builder {
       };
       const int conv_total = std::max((fm.L1 - 1) * 2 + 7 - S, 0);
       const int pool_total = std::max((L2 - 1) * 2 + 3 - fm.L1, 0);
-      // the fused front end exists for the single 16-bit modes; the split mode runs the stem on the CUDA cores in fp32
-      // (exact hi + lo of its output) followed by conv2 / conv3 as generic GEMM launches
-      const bool front = TC && !SPLIT && opt.fused_front != 0;
+      // un-fused reference (fused_front = 0): stem on the CUDA cores in fp32 followed by conv2 / conv3 as generic GEMM launches
+      const bool front = TC && opt.fused_front != 0;
       T* wB1 = reinterpret_cast<T*>(wa.take((size_t)192 * 64 * sizeof(T)));
       if (front) {
         if constexpr (TC) {
@@ -271,6 +270,8 @@ struct Builder {
             const bool f16 = std::is_same<T, __half>::value;
             FrontLaunch& Q = st.front;
             Q.fp16 = f16;
+            Q.split = SPLIT;
+            Q.p.lo_x0 = loX;
             encode_map_16(&Q.maps.w2, Wc2.w, 128, Wc2.Ktot, Wc2.Ktot, 128, 64, f16);
             if (Wc3.N != 256 || Wc2.N != 128) fail(DSB_ERR_STATE, "internal: front kernel expects conv2 N=128, conv3 N=256");
             encode_map_16(&Q.maps.w3, Wc3.w, 256, Wc3.Ktot, Wc3.Ktot, 128, 32, f16);

@@ -60,7 +60,19 @@ template <bool F16> __device__ __forceinline__ float from16(uint16_t h) {
   else return __uint_as_float((uint32_t)h << 16);
 }
 
-template <bool F16>
+// lo part of a packed pair of fp32 values whose hi parts are already packed in `hi` (split-operand mode, fp16)
+__device__ __forceinline__ uint32_t pack_lo(float a, float b, uint32_t hi) {
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  return *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// SPLIT (DSB_PREC_FP16X2): P1, C2 and X0 are (hi, lo) fp16 pairs, the weights stay single fp16 and every conv is
+// [xh | xl] . [W ; W].  Shared memory has no room for a second P1 / C2 tile, so the hi tile and the lo tile of a stage go
+// through the SAME buffer one after the other: the staging warps read the accumulator from TMEM twice (first pass packs
+// the hi parts, second pass the lo parts) and the MMA thread interleaves the stages so that neither pass waits on an MMA
+// that is issued behind it:   conv3(k-2).hi  conv2(k-1).hi  conv3(k-2).lo[0,1]  conv2(k-1).lo  conv3(k-2).lo[2,3]  conv1(k)
+template <bool F16, bool SPLIT>
 __global__ void __launch_bounds__(G_THREADS, 1)
 front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ FrontParams p, const int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -154,10 +166,49 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
         }
         tc_commit(bar(ACC3_FULL));
       };
+      // split mode: part 0 = hi tile, part 1 = lo tile of the same buffer (fill number 2k + part of its barrier pair)
+      auto mma2s = [&](int k, int part) {
+        if (part == 0) mbar_wait(bar(ACC2_EMPTY), ((uint32_t)k & 1u) ^ 1u);
+        mbar_wait(bar(P1_FULL), (uint32_t)(2 * k + part) & 1u);
+        tc_fence_after();
+        const uint64_t ad = make_kmajor_desc<64>(base + GSmem::p1);
+        const uint64_t bd = make_kmajor_desc<64>(base + GSmem::w2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tc_mma_bf16(tmem_base + ACC2, ad + 2 * j, bd + 2 * j, id128, (part | j) != 0 ? 1u : 0u);
+        tc_commit(bar(P1_EMPTY));
+        if (part == 1) tc_commit(bar(ACC2_FULL));
+      };
+      auto mma3s = [&](int k, int part, int kb0, int kb1) {
+        if (part == 0 && kb0 == 0) mbar_wait(bar(ACC3_EMPTY), ((uint32_t)k & 1u) ^ 1u);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar(C2_FULL + kb), (uint32_t)(2 * k + part) & 1u);
+          tc_fence_after();
+          for (int tap = 0; tap < 3; ++tap) {
+            const uint64_t ad = make_kmajor_desc<32>(base + GSmem::c2 + kb * G_C2_KB + (uint32_t)tap * 64u);
+            const uint64_t bd = make_kmajor_desc<32>(base + GSmem::w3 + (tap * 4 + kb) * G_W3_BLK);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tc_mma_bf16(tmem_base + ACC3, ad + 2 * j, bd + 2 * j, id128, (part | tap | kb | j) != 0 ? 1u : 0u);
+          }
+          tc_commit(bar(C2_EMPTY + kb));
+        }
+        if (part == 1 && kb1 == 4) tc_commit(bar(ACC3_FULL));
+      };
       for (int it = 0; it < my_tiles + 2; ++it) {
-        if (it < my_tiles) mma1(it);
-        if (it >= 1 && it - 1 < my_tiles) mma2(it - 1);
-        if (it >= 2) mma3(it - 2);
+        if constexpr (SPLIT) {
+          const bool c3 = it >= 2, c2 = it >= 1 && it - 1 < my_tiles;
+          // conv2's lo part (and with it ACC2_FULL of the next tile) goes out in the middle of conv3's lo part: the C2
+          // staging of the next tile then overlaps the second half of these MMAs instead of starting after all of them
+          if (c3) mma3s(it - 2, 0, 0, 4);
+          if (c2) mma2s(it - 1, 0);
+          if (c3) mma3s(it - 2, 1, 0, 2);
+          if (c2) mma2s(it - 1, 1);
+          if (c3) mma3s(it - 2, 1, 2, 4);
+          if (it < my_tiles) mma1(it);
+        } else {
+          if (it < my_tiles) mma1(it);
+          if (it >= 1 && it - 1 < my_tiles) mma2(it - 1);
+          if (it >= 2) mma3(it - 2);
+        }
       }
     }
   } else if (warp < 6) {
@@ -217,35 +268,41 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
       const float NEG = -3.0e38f;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
       mbar_wait(bar(ACC1_FULL), ph);
-      mbar_wait(bar(P1_EMPTY), ph ^ 1u);
-      tc_fence_after();
       const uint32_t rowp = base + GSmem::p1 + (uint32_t)i * 128u;
+      constexpr int PARTS = SPLIT ? 2 : 1;
 #pragma unroll 1
-      for (int cg = 0; cg < 4; ++cg) {                    // 16 channels at a time
-        uint32_t a0[16], a1[16], a2[16];
-        tc_ld16(t_row + (uint32_t)(cg * 16), a0);
-        tc_ld16(t_row + (uint32_t)(64 + cg * 16), a1);
-        tc_ld16(t_row + (uint32_t)(128 + cg * 16), a2);
-        tc_wait_ld();
-        uint32_t pk[8];
+      for (int part = 0; part < PARTS; ++part) {
+        // fill number kk (single) or 2 kk + part (split) of the P1 tile: wait until the conv2 MMAs of the previous fill have read it
+        mbar_wait(bar(P1_EMPTY), ((uint32_t)(PARTS * kk + part) & 1u) ^ 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cg = 0; cg < 4; ++cg) {                    // 16 channels at a time (unrolling this loop measured slower)
+          uint32_t a0[16], a1[16], a2[16];
+          tc_ld16(t_row + (uint32_t)(cg * 16), a0);
+          tc_ld16(t_row + (uint32_t)(64 + cg * 16), a1);
+          tc_ld16(t_row + (uint32_t)(128 + cg * 16), a2);
+          tc_wait_ld();
+          uint32_t pk[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float v[2];
+          for (int k = 0; k < 8; ++k) {
+            float v[2];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = 2 * k + e;
-            const float m = fmaxf(ok0 ? __uint_as_float(a0[c]) : NEG, fmaxf(ok1 ? __uint_as_float(a1[c]) : NEG, ok2 ? __uint_as_float(a2[c]) : NEG));
-            v[e] = (ok0 || ok1 || ok2) ? relu_keep_nan(m + p.b1v[cg * 16 + c]) : 0.f;
+            for (int e = 0; e < 2; ++e) {
+              const int c = 2 * k + e;
+              const float m = fmaxf(ok0 ? __uint_as_float(a0[c]) : NEG, fmaxf(ok1 ? __uint_as_float(a1[c]) : NEG, ok2 ? __uint_as_float(a2[c]) : NEG));
+              v[e] = (ok0 || ok1 || ok2) ? relu_keep_nan(m + p.b1v[cg * 16 + c]) : 0.f;
+            }
+            pk[k] = pack16<F16>(v[0], v[1]);
+            if (SPLIT && part == 1) pk[k] = pack_lo(v[0], v[1], pk[k]);
           }
-          pk[k] = pack16<F16>(v[0], v[1]);
+          sts128(rowp + ((((uint32_t)(2 * cg)) ^ ((uint32_t)i & 7u)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          sts128(rowp + ((((uint32_t)(2 * cg + 1)) ^ ((uint32_t)i & 7u)) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
         }
-        sts128(rowp + ((((uint32_t)(2 * cg)) ^ ((uint32_t)i & 7u)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-        sts128(rowp + ((((uint32_t)(2 * cg + 1)) ^ ((uint32_t)i & 7u)) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(bar(P1_FULL)); if (part == PARTS - 1) mbar_arrive(bar(ACC1_EMPTY)); }
       }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(bar(P1_FULL)); mbar_arrive(bar(ACC1_EMPTY)); }
     }
   } else if (warp < 14) {
     // ---------------- C2 staging warps: relu(conv2 + bias) -> 16-bit A operand of conv3 ----------------
@@ -261,35 +318,44 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + ACC2;
       mbar_wait(bar(ACC2_FULL), ph);
       tc_fence_after();
-#pragma unroll 1
-      for (int kb = 0; kb < 4; ++kb) {
-        uint32_t r2[2][16];
-        tc_ld16(t_row + (uint32_t)(kb * 32), r2[0]);
-        tc_ld16(t_row + (uint32_t)(kb * 32 + 16), r2[1]);
-        tc_wait_ld();
-        if (kb == 3) {                                       // conv2's accumulator is in registers: conv2 of the next tile may start
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(ACC2_EMPTY));
-        }
-        mbar_wait(bar(C2_EMPTY + kb), ph ^ 1u);
-        const uint32_t ub = base + GSmem::c2 + kb * G_C2_KB + rr * 64u;
+      constexpr int PARTS = SPLIT ? 2 : 1;
+      const uint32_t keep = zero ? 0u : 0xffffffffu;
+      // fully unrolled: the bias then comes straight from the constant bank as an instruction operand (an indexed
+      // p.b2v[kb * 32 + e] costs one LDC per element, and this stage is what paces the kernel in split mode)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[4];
+      for (int part = 0; part < PARTS; ++part) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int e = c * 8 + 2 * k;
-            float a = relu_keep_nan(__uint_as_float(r2[e >> 4][e & 15]) + p.b2v[kb * 32 + e]);
-            float d = relu_keep_nan(__uint_as_float(r2[(e + 1) >> 4][(e + 1) & 15]) + p.b2v[kb * 32 + e + 1]);
-            if (zero) { a = 0.f; d = 0.f; }
-            pk[k] = pack16<F16>(a, d);
+        for (int kb = 0; kb < 4; ++kb) {
+          uint32_t r2[2][16];
+          tc_ld16(t_row + (uint32_t)(kb * 32), r2[0]);
+          tc_ld16(t_row + (uint32_t)(kb * 32 + 16), r2[1]);
+          tc_wait_ld();
+          if (kb == 3 && part == PARTS - 1) {                  // conv2's accumulator is in registers: conv2 of the next tile may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(ACC2_EMPTY));
           }
-          sts128(ub + (((uint32_t)c ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          // fill number kk (single) or 2 kk + part (split) of this k-block: its previous fill has been read by the conv3 MMAs
+          mbar_wait(bar(C2_EMPTY + kb), ((uint32_t)(PARTS * kk + part) & 1u) ^ 1u);
+          const uint32_t ub = base + GSmem::c2 + kb * G_C2_KB + rr * 64u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = c * 8 + 2 * k;
+              const float a = relu_keep_nan(__uint_as_float(r2[e >> 4][e & 15]) + p.b2v[kb * 32 + e]);
+              const float d = relu_keep_nan(__uint_as_float(r2[(e + 1) >> 4][(e + 1) & 15]) + p.b2v[kb * 32 + e + 1]);
+              pk[k] = pack16<F16>(a, d);
+              if (SPLIT && part == 1) pk[k] = pack_lo(a, d, pk[k]);
+              pk[k] &= keep;                               // halo / out-of-range rows are the zero padding of conv3
+            }
+            sts128(ub + (((uint32_t)c ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(C2_FULL + kb));
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(C2_FULL + kb));
       }
     }
   } else {
@@ -309,32 +375,43 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + ACC3;
       mbar_wait(bar(ACC3_FULL), ph);
       tc_fence_after();
-      for (int g = half; g < 4; g += 2) {
-        uint32_t r2[2][16];
-        __syncwarp();
-        tc_ld16(t_row + (uint32_t)(g * 32), r2[0]);
-        tc_ld16(t_row + (uint32_t)(g * 32 + 16), r2[1]);
-        tc_wait_ld();
-        if (g + 2 >= 4) {                                  // last group of this warp: the accumulator is in registers
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(ACC3_EMPTY));
-        }
-        uint32_t pk[16];
+      // both 32-column groups of this warp are read before any arithmetic, so that the conv3 MMAs of the next tile (the
+      // accumulator is single-buffered: TMEM holds conv1 192 + conv2 128 + conv3 128 columns) wait for two TMEM loads, not
+      // for the first group's stores
+      uint32_t racc[2][2][16];
+      __syncwarp();
+#pragma unroll
+      for (int gi = 0; gi < 2; ++gi) {
+        tc_ld16(t_row + (uint32_t)((half + 2 * gi) * 32), racc[gi][0]);
+        tc_ld16(t_row + (uint32_t)((half + 2 * gi) * 32 + 16), racc[gi][1]);
+      }
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(ACC3_EMPTY));
+#pragma unroll
+      for (int gi = 0; gi < 2; ++gi) {
+        const int g = half + 2 * gi;
+        uint32_t pk[16], pl[16];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           const int col = g * 32 + 16 * h2;
           float v[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r2[h2][k]) + p.b3v[nh * 128 + col + k];
+          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(racc[gi][h2][k]) + p.b3v[nh * 128 + col + k];
 #pragma unroll
           for (int k = 0; k < 16; ++k) v[k] = halo ? 0.f : relu_keep_nan(v[k]);
 #pragma unroll
           for (int k = 0; k < 8; ++k) pk[8 * h2 + k] = pack16<F16>(v[2 * k], v[2 * k + 1]);
+          if constexpr (SPLIT) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pl[8 * h2 + k] = pack_lo(v[2 * k], v[2 * k + 1], pk[8 * h2 + k]);
+          }
         }
         const size_t pitch = (size_t)p.ldX * 2;
         uint8_t* dst = reinterpret_cast<uint8_t*>(p.X0) + (ptrdiff_t)wrow0 * (ptrdiff_t)pitch + (size_t)(nh * 128 + g * 32) * 2;
         staged_store<4>(stage, pk, lane, ok_mask, dst, pitch);
+        if constexpr (SPLIT) staged_store<4>(stage, pl, lane, ok_mask, dst + p.lo_x0 * 2, pitch);
       }
     }
   }
@@ -359,13 +436,15 @@ void launch_front2(const FrontLaunch& L, const float* signals, int n, int sm_cou
   if (grid > 2 * num_tiles) grid = 2 * num_tiles;
   if (grid < 2) grid = 2;
   const size_t smem = GSmem::total + 1024;
-  static bool cfg[2][64] = {{false}};
+  static bool cfg[3][64] = {{false}};
   int dev = 0;
   DSB_CUDA(cudaGetDevice(&dev));
-  auto kern = L.fp16 ? front2_kernel<true> : front2_kernel<false>;
-  if (!cfg[L.fp16 ? 1 : 0][dev & 63]) {
+  if (L.split && !L.fp16) fail(DSB_ERR_STATE, "internal: the split front end is fp16 only");
+  auto kern = L.split ? front2_kernel<true, true> : L.fp16 ? front2_kernel<true, false> : front2_kernel<false, false>;
+  const int which = L.split ? 2 : L.fp16 ? 1 : 0;
+  if (!cfg[which][dev & 63]) {
     DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    cfg[L.fp16 ? 1 : 0][dev & 63] = true;
+    cfg[which][dev & 63] = true;
   }
   launch_pdl(kern, grid, G_THREADS, smem, s, L.maps, p, num_tiles);
   DSB_CUDA(cudaGetLastError());

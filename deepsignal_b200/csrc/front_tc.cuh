@@ -25,11 +25,12 @@ struct FrontParams {
   int L1 = 0, L = 0, Lp = 0;        // conv1 output length, pooled length (90), padded rows per sample (92)
   int conv_pl = 0, pool_pl = 0;     // SAME-padding left pads
   void* X0 = nullptr; int ldX = 0;  // [n*Lp][ldX]
+  long long lo_x0 = 0;              // element offset X0 -> its lo twin (split mode)
   int M = 0;                        // n * Lp
   float b1v[64]; float b2v[128]; float b3v[256];   // front2: biases by value (constant bank)
 };
 
-struct FrontLaunch { FrontMaps maps; FrontParams p; bool fp16 = false; };
+struct FrontLaunch { FrontMaps maps; FrontParams p; bool fp16 = false; bool split = false; };
 
 constexpr int FRONT_TILE_ROWS = 126;   // 128-row tiles overlap by one row on each side (conv3 halo)
 
