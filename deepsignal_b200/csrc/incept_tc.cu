@@ -60,7 +60,10 @@ __device__ __forceinline__ uint32_t idesc_f16(bool f16, int n) {
 // Kernel A
 // ============================================================================================
 constexpr int A_THREADS = 448;       // warp 0 TMA, warp 1 MMA, warps 2-5 pool, warps 6-13 epilogue
-constexpr int A_SLOTS = 5;
+#ifndef DSB_A_SLOTS
+#define DSB_A_SLOTS 5
+#endif
+constexpr int A_SLOTS = DSB_A_SLOTS;
 constexpr uint32_t A_SLOT_BYTES = 128 * 64 * 2;        // one [128 x 64] SWIZZLE_128B tile
 constexpr uint32_t A_WP1_BLK = 192 * 64 * 2;           // 24576
 constexpr uint32_t A_WB1_BLK = 48 * 64 * 2;            // 6144
@@ -160,8 +163,10 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const __grid_constant_
               tc_fence_after();
               const uint64_t ad = make_kmajor_desc<64>(base + ASmem::ring + sp * A_SLOT_BYTES);
               const uint64_t bd = make_kmajor_desc<64>(base + ASmem::wp1 + step * A_WP1_BLK);
+              if (!((p.ablate & 16) && part == 1)) {         // ablate 16 (timing only): no lo-part p1 MMAs
 #pragma unroll
-              for (int k = 0; k < 4; ++k) tc_mma_bf16(d_p1, ad + 2 * k, bd + 2 * k, id_p1, (step | part | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) tc_mma_bf16(d_p1, ad + 2 * k, bd + 2 * k, id_p1, (step | part | k) != 0 ? 1u : 0u);
+              }
               tc_commit(p1_done(sp));
               if (++sp == A_SLOTS) { sp = 0; php ^= 1u; }
             }
@@ -174,8 +179,10 @@ incept_a_kernel(const __grid_constant__ InceptAMaps maps, const __grid_constant_
               tc_fence_after();
               const uint64_t ad = make_kmajor_desc<64>(base + ASmem::ring + sb * A_SLOT_BYTES);
               const uint64_t bd = make_kmajor_desc<64>(base + ASmem::wb1 + j * A_WB1_BLK);
+              if (!(p.ablate & 8)) {                         // ablate 8 (timing only): no b1 MMAs
 #pragma unroll
-              for (int k = 0; k < 4; ++k) tc_mma_bf16(d_b1, ad + 2 * k, bd + 2 * k, id_b1, (j | part | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) tc_mma_bf16(d_b1, ad + 2 * k, bd + 2 * k, id_b1, (j | part | k) != 0 ? 1u : 0u);
+              }
               tc_commit(empty(sb));
               if (++sb == A_SLOTS) { sb = 0; phb ^= 1u; }
             }

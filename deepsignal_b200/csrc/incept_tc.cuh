@@ -49,7 +49,8 @@ struct InceptBLaunch { InceptBMaps maps; InceptBParams p; bool fp16 = false; boo
 
 constexpr int INCEPT_A_TILE_ROWS = 126;   // 128-row tiles overlap by one row on each side (pool halo)
 
-// ablate: timing experiments only (dsb_plan_options): 1 skip pool / staging math, 2 skip epilogue stores, 4 (kernel A) skip the whole epilogue
+// ablate: timing experiments only (dsb_plan_options): 1 skip pool / staging math, 2 skip epilogue stores, 4 (kernel A) skip the whole epilogue,
+// 8 (kernel A) no b1 MMAs, 16 (kernel A) no lo-part p1 MMAs
 void launch_incept_a(const InceptALaunch& L, int M, int sm_count, int ablate, cudaStream_t s);
 void launch_incept_b(const InceptBLaunch& L, int M, int sm_count, int ablate, cudaStream_t s);
 
