@@ -289,6 +289,7 @@ struct Builder {
                   const size_t row = (size_t)(a * 64 + c) * 64;
                   const int k = 2 * a + t;
                   hB1[row + k] = wh; hB1[row + 11 + k] = wh; hB1[row + 22 + k] = wl;
+                  hB1[row + 33 + a] = __float2half_rn(1.f);      // picks up the kernel's out-of-range penalty of pool tap a
                 }
             DSB_CUDA(cudaMemcpyAsync(wB1, hB1.data(), hB1.size() * sizeof(__half), cudaMemcpyHostToDevice, up_stream));
             DSB_CUDA(cudaStreamSynchronize(up_stream));

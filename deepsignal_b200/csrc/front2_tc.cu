@@ -238,6 +238,14 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
           h[k] = xh; h[11 + k] = xl; h[22 + k] = xh;
         }
       }
+      {
+        // columns 33..35 meet a 1.0 in the conv1 operand rows of pool tap 0 / 1 / 2: a tap that lies outside the conv1
+        // output (SAME padding of the pool), and every tap of a halo row, gets -65504 added, so the pool's max ignores it
+        // and relu(max + bias) of a halo row is 0 without any per-element select in the pool staging warps
+        const int q0 = 2 * pos - p.pool_pl;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) h[33 + a] = (valid && q0 + a >= 0 && q0 + a < p.L1) ? (uint16_t)0 : (uint16_t)0xFBFF;
+      }
       mbar_wait(bar(A1_EMPTY), ((uint32_t)kk & 1u) ^ 1u);
       const uint32_t rowp = base + GSmem::a1 + (uint32_t)i * 128u;
 #pragma unroll
@@ -263,20 +271,21 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
       const int s = valid ? r / p.Lp : 0;
       const int pos = r - s * p.Lp;
       valid = valid && pos < p.L;
-      const int q0 = 2 * pos - p.pool_pl;
-      const bool ok0 = valid && q0 >= 0 && q0 < p.L1, ok1 = valid && q0 + 1 >= 0 && q0 + 1 < p.L1, ok2 = valid && q0 + 2 >= 0 && q0 + 2 < p.L1;
-      const float NEG = -3.0e38f;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+      (void)valid;
       mbar_wait(bar(ACC1_FULL), ph);
       const uint32_t rowp = base + GSmem::p1 + (uint32_t)i * 128u;
       constexpr int PARTS = SPLIT ? 2 : 1;
+      // split mode: two passes over the accumulator (hi parts, then lo parts into the same tile).  Keeping the 32 lo
+      // registers of a row across the wait instead measured slower (spills: the kernel runs at 80 registers per thread).
 #pragma unroll 1
       for (int part = 0; part < PARTS; ++part) {
         // fill number kk (single) or 2 kk + part (split) of the P1 tile: wait until the conv2 MMAs of the previous fill have read it
         mbar_wait(bar(P1_EMPTY), ((uint32_t)(PARTS * kk + part) & 1u) ^ 1u);
         tc_fence_after();
 #pragma unroll 1
-        for (int cg = 0; cg < 4; ++cg) {                    // 16 channels at a time (unrolling this loop measured slower)
+        for (int cg = 0; cg < 4; ++cg) {                    // 16 channels at a time
+          // taps outside the conv1 output (and whole halo rows) carry the -65504 penalty of the im2col tile: no selects here
           uint32_t a0[16], a1[16], a2[16];
           tc_ld16(t_row + (uint32_t)(cg * 16), a0);
           tc_ld16(t_row + (uint32_t)(64 + cg * 16), a1);
@@ -289,8 +298,8 @@ front2_kernel(const __grid_constant__ FrontMaps maps, const __grid_constant__ Fr
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int c = 2 * k + e;
-              const float m = fmaxf(ok0 ? __uint_as_float(a0[c]) : NEG, fmaxf(ok1 ? __uint_as_float(a1[c]) : NEG, ok2 ? __uint_as_float(a2[c]) : NEG));
-              v[e] = (ok0 || ok1 || ok2) ? relu_keep_nan(m + p.b1v[cg * 16 + c]) : 0.f;
+              const float m = fmaxf(__uint_as_float(a0[c]), fmaxf(__uint_as_float(a1[c]), __uint_as_float(a2[c])));
+              v[e] = relu_keep_nan(m + p.b1v[cg * 16 + c]);
             }
             pk[k] = pack16<F16>(v[0], v[1]);
             if (SPLIT && part == 1) pk[k] = pack_lo(v[0], v[1], pk[k]);
