@@ -25,8 +25,14 @@ tests/test_model_oracle.py:
   probs = sigmoid(logits); prediction = argmax (ties -> 0) (model.py:100,108).
 
 PARITY PIN STATUS: the reference ships no golden vectors / known-answer tests for
-this path and TF cannot run here, so the model oracle is pinned
-only by those hand-computed cases: **parity unpinned** against real TF output.
+this path and TF cannot run here.  The WIRING of this restatement is
+pinned to the reference's own source: tests/golden/make_model_golden.py executes
+deepsignal/model.py + layers.py UNMODIFIED over a NumPy stand-in for the ~35 TF 1.x
+calls they make (oracle/tf_shim.py, written independently of this file), and
+tests/test_model_golden.py requires this oracle to reproduce those outputs to 1e-10
+on two checkpoints, with exactly the 580 variable names the reference's scopes
+generate.  The TF op semantics themselves (the bullets above) remain restated and
+hand-checked only: **parity unpinned against real TF kernels**.
 """
 from __future__ import annotations
 
