@@ -246,9 +246,10 @@ template <class F> __device__ double pairwise_block(const F& f, int a0, int n) {
   for (; i < n; ++i) res = __dadd_rn(res, f(a0 + i));
   return res;
 }
-// The n > 128 recursion of numpy (split at n/2 rounded down to a multiple of 8) with an explicit stack.
-template <class F> __device__ double pairwise_sum(const F& f, int a0, int n) {
-  if (n <= 128) return pairwise_block(f, a0, n);
+// The n > 128 recursion of numpy (split at n/2 rounded down to a multiple of 8) with an explicit stack; `leaf(a0, n)`
+// evaluates one block of at most 128 elements.
+template <class Leaf> __device__ double pairwise_tree(int a0, int n, Leaf&& leaf) {
+  if (n <= 128) return leaf(a0, n);
   struct Frame { int a0, n, state; double left; };
   Frame st[26];
   int sp = 0;
@@ -256,7 +257,7 @@ template <class F> __device__ double pairwise_sum(const F& f, int a0, int n) {
   double ret = 0.0;
   while (sp >= 0) {
     Frame& fr = st[sp];
-    if (fr.n <= 128) { ret = pairwise_block(f, fr.a0, fr.n); --sp; continue; }
+    if (fr.n <= 128) { ret = leaf(fr.a0, fr.n); --sp; continue; }
     int n2 = fr.n / 2;
     n2 -= n2 % 8;
     if (fr.state == 0) { fr.state = 1; st[sp + 1] = Frame{fr.a0, n2, 0, 0.0}; ++sp; continue; }
@@ -265,6 +266,30 @@ template <class F> __device__ double pairwise_sum(const F& f, int a0, int n) {
     --sp;
   }
   return ret;
+}
+// A slice of more than 128 samples, summed by a whole warp (all 32 lanes call it with the same arguments): lane 0 lists
+// the leaf blocks of the split tree, the lanes sum one leaf each with the eight-accumulator scheme, lane 0 adds the leaf
+// sums in the tree's order.  Every addition is the one the serial recursion performs, so the result is bit-identical -- but
+// a 3,000-sample stall costs ~100 dependent additions per lane instead of 3,000 on one lane while 31 wait (and a 100,000-
+// sample one no longer holds a warp for milliseconds).
+constexpr int LEAF_CAP = 128;
+struct LeafScratch { int a0[LEAF_CAP]; short len[LEAF_CAP]; double sum[LEAF_CAP]; };
+template <class F> __device__ double pairwise_sum_warp(const F& f, int n, int lane, LeafScratch& sc) {
+  int L = 0;
+  if (lane == 0)
+    pairwise_tree(0, n, [&](int a, int m) { if (L < LEAF_CAP) { sc.a0[L] = a; sc.len[L] = (short)m; } ++L; return 0.0; });
+  L = __shfl_sync(0xffffffffu, L, 0);
+  double r = 0.0;
+  if (L > LEAF_CAP) {                                   // more than ~12 k samples in one base: serial on lane 0
+    if (lane == 0) r = pairwise_tree(0, n, [&](int a, int m) { return pairwise_block(f, a, m); });
+    return __shfl_sync(0xffffffffu, r, 0);
+  }
+  __syncwarp();
+  for (int k = lane; k < L; k += 32) sc.sum[k] = pairwise_block(f, sc.a0[k], sc.len[k]);
+  __syncwarp();
+  if (lane == 0) { int k = 0; r = pairwise_tree(0, n, [&](int, int) { return sc.sum[k++]; }); }
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, r, 0);
 }
 
 struct NormAt {
@@ -394,10 +419,12 @@ __device__ __forceinline__ int base_code(uint8_t c) {
 
 constexpr int SITE_WARPS = 8;
 constexpr int MAX_KLEN = 33;
+constexpr int LONG_BASE = 128;       // slices longer than this are summed by the whole warp (pairwise_sum_warp)
 
 __global__ void __launch_bounds__(SITE_WARPS * 32) site_feature_kernel(const SiteParams p) {
   __shared__ int cum_s[SITE_WARPS][MAX_KLEN + 1];
   __shared__ int st_s[SITE_WARPS][MAX_KLEN];
+  __shared__ LeafScratch leaf_s[SITE_WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t site = (int64_t)blockIdx.x * SITE_WARPS + w;
   if (site >= p.n_sites) return;
@@ -411,6 +438,12 @@ __global__ void __launch_bounds__(SITE_WARPS * 32) site_feature_kernel(const Sit
   int* st = st_s[w];
   // per-base gathers; K <= 33 -> up to two bases per lane
   const double* lut = p.lut + p.lut_off[r] - p.vmin[r];
+  auto put_stats = [&](int j, double mu, double sd) {
+    if (p.out.means) p.out.means[site * K + j] = (float)mu;
+    if (p.out.stds) p.out.stds[site * K + j] = (float)sd;
+    if (p.out.means64) p.out.means64[site * K + j] = mu;
+    if (p.out.stds64) p.out.stds64[site * K + j] = sd;
+  };
   for (int j = lane; j < K; j += 32) {
     const int64_t e = e0 + loc - nbh + j;
     // python slice norm[s : s+l] for s >= 0 (negative starts are rejected on the host side), then np.mean / np.std of it
@@ -424,19 +457,27 @@ __global__ void __launch_bounds__(SITE_WARPS * 32) site_feature_kernel(const Sit
     cum[j + 1] = len;
     const int code = base_code(p.rd.ev_base[e]);
     if (p.out.kmer) p.out.kmer[site * K + j] = code;
+    if (p.out.lens) p.out.lens[site * K + j] = (float)len;
+    if (p.out.lens_i32) p.out.lens_i32[site * K + j] = len;
+    if (len > LONG_BASE) continue;                          // stalls: summed by the whole warp below
     double mu = nan(""), sd = nan("");                      // np.mean([]) -> nan
     if (len > 0) {
       NormAt f{x + s, lut};
-      mu = __ddiv_rn(pairwise_sum(f, 0, len), (double)len);
+      mu = __ddiv_rn(pairwise_block(f, 0, len), (double)len);
       SqDevAt g{f, mu};
-      sd = sqrt(__ddiv_rn(pairwise_sum(g, 0, len), (double)len));
+      sd = sqrt(__ddiv_rn(pairwise_block(g, 0, len), (double)len));
     }
-    if (p.out.means) p.out.means[site * K + j] = (float)mu;
-    if (p.out.stds) p.out.stds[site * K + j] = (float)sd;
-    if (p.out.lens) p.out.lens[site * K + j] = (float)len;
-    if (p.out.means64) p.out.means64[site * K + j] = mu;
-    if (p.out.stds64) p.out.stds64[site * K + j] = sd;
-    if (p.out.lens_i32) p.out.lens_i32[site * K + j] = len;
+    put_stats(j, mu, sd);
+  }
+  __syncwarp();
+  for (int j = 0; j < K; ++j) {                             // warp-uniform: st[] / cum[] are shared
+    const int len = cum[j + 1];                             // (still the slice length: the prefix sum follows)
+    if (len <= LONG_BASE) continue;
+    NormAt f{x + st[j], lut};
+    const double mu = __ddiv_rn(pairwise_sum_warp(f, len, lane, leaf_s[w]), (double)len);
+    SqDevAt g{f, mu};
+    const double sd = sqrt(__ddiv_rn(pairwise_sum_warp(g, len, lane, leaf_s[w]), (double)len));
+    if (lane == 0) put_stats(j, mu, sd);
   }
   __syncwarp();
   if (lane == 0) {
@@ -470,17 +511,20 @@ __global__ void __launch_bounds__(SITE_WARPS * 32) site_feature_kernel(const Sit
   if (lane == 0 && p.out.window) {
     p.out.window[site * 3] = mode; p.out.window[site * 3 + 1] = start; p.out.window[site * 3 + 2] = nreal;
   }
+  float* sig32 = p.out.signals ? p.out.signals + site * S : nullptr;
+  double* sig64 = p.out.signals64 ? p.out.signals64 + site * S : nullptr;
+  int b = mode == 1 ? mid : 0;                              // q is non-decreasing in j: the base pointer only moves forward
   for (int j = lane; j < S; j += 32) {
     double v = 0.0;
     if (j < nreal) {
-      // concatenated index q -> (base b, offset)
-      const int q = (mode == 1) ? start + (int)(((int64_t)j * midlen) / S) : start + j;
-      int b = 0;
-      while (b + 1 < K && cum[b + 1] <= q) ++b;
+      // concatenated index q -> (base b, offset); mode 1 resamples the middle base (64-bit product)
+      int q = start + j;
+      if (mode == 1) q = start + (int)(((int64_t)j * midlen) / S);
+      else while (b + 1 < K && cum[b + 1] <= q) ++b;
       v = __ldg(lut + x[st[b] + (q - cum[b])]);
     }
-    if (p.out.signals) p.out.signals[site * S + j] = (float)v;
-    if (p.out.signals64) p.out.signals64[site * S + j] = v;
+    if (sig32) sig32[j] = (float)v;
+    if (sig64) sig64[j] = v;
   }
 }
 
