@@ -115,12 +115,13 @@ CONTIGS = {"chrSynA": 5_000_000, "chrSynB": 3_000_000, "chrSynC": 2_000_000, "ch
 
 
 def synth_reads(n_reads: int, seed: int = SEED_CFG2, nb_lo: int = 1500, nb_hi: int = 4500,
-                cg_frac: float = 0.01, long_stall_frac: float = 0.002, with_reference: bool = True) -> ReadBatch:
+                cg_frac: float = 0.01, long_stall_frac: float = 0.002, with_reference: bool = True,
+                force_lens: dict | None = None) -> ReadBatch:
     """cfg-2 / cfg-4 generator: CpG-depleted sequence (~``cg_frac`` CG dinucleotides,
     ~30 sites per 3 kb read), 4-level current table + N(0, 12 ADC) noise around 480,
     contiguous events after a random ``read_start_rel_to_raw`` lead-in.  ``long_stall_frac``
     of the bases dwell 360..700 samples so every branch of the 360-sample window rule
-    (extract_features.py:154-190) is exercised."""
+    (extract_features.py:154-190) is exercised.  ``force_lens`` = {global event index: samples}."""
     rng = np.random.default_rng(seed)
     nb = rng.integers(nb_lo, nb_hi + 1, size=n_reads)
     ev_off = np.zeros(n_reads + 1, np.int64)
@@ -137,6 +138,8 @@ def synth_reads(n_reads: int, seed: int = SEED_CFG2, nb_lo: int = 1500, nb_hi: i
     ev_len = _dwell(rng, total_ev)
     long_stall = rng.random(total_ev) < long_stall_frac
     ev_len[long_stall] = rng.integers(360, 701, size=int(long_stall.sum()))
+    for ev_index, n_samples in (force_lens or {}).items():      # tests: exact dwell of chosen events (draws nothing from rng)
+        ev_len[ev_index] = n_samples
     lead = rng.integers(0, 2001, size=n_reads)
     tail = rng.integers(0, 200, size=n_reads)
     csum = np.zeros(total_ev + 1, np.int64)

@@ -1,0 +1,12 @@
+#!/usr/bin/env bash
+# GPU session r2ah: final-state evidence: full GPU test suite, smoke, extraction profile + launch list + capture, bench lines (own arm, reference arm)
+set -u
+O=gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 120 python profiles/prof_extract.py | tee $O/r2ah_extract.json
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/r2ah_launches_extract.csv python profiles/prof_extract.py > /dev/null 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:site_feature_kernel -s 2 -c 1 -f -o $O/r2ah_full_site_feature python profiles/prof_extract.py > /dev/null 2>&1
+timeout 900 python bench.py > $O/r2ah_bench_n1.json 2> $O/r2ah_bench_n1.err; tail -c 200 $O/r2ah_bench_n1.err; head -c 200 $O/r2ah_bench_n1.json; echo
+timeout 900 python bench.py --impl reference > $O/r2ah_bench_ref.json 2> $O/r2ah_bench_ref.err; tail -c 200 $O/r2ah_bench_ref.err; head -c 400 $O/r2ah_bench_ref.json; echo
+ls -la $O | grep r2ah

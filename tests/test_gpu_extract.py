@@ -140,6 +140,20 @@ def test_edge_cases(engine):
     assert got["n_sites"] == 0
 
 
+def test_very_long_slices_are_bit_identical(engine):
+    """Stalls of hundreds to tens of thousands of samples: summed by the whole warp (leaf blocks of numpy's pairwise tree in
+    parallel, combined in tree order) and, beyond the leaf scratch, serially -- np.mean / np.std must still match bit for bit."""
+    force = {30: 129, 31: 128, 60: 1000, 61: 257, 90: 5000, 120: 20000, 150: 40000}
+    rb = synth_reads(2, seed=83, nb_lo=180, nb_hi=220, cg_frac=0.08, force_lens=force)
+    got = engine.extract(rb, ["CG"])
+    want = _oracle(rb, ["CG"])
+    _compare(got, want)
+    lens = np.asarray([w[10] for w in want])
+    assert lens.max() == 40000 and (lens == 20000).any() and (lens == 5000).any() and (lens == 129).any()
+    assert np.array_equal(got["means64"], np.asarray([w[8] for w in want]), equal_nan=True)
+    assert np.array_equal(got["stds64"], np.asarray([w[9] for w in want]), equal_nan=True)
+
+
 def test_wide_adc_range_uses_global_histogram(engine):
     rb = synth_reads(4, seed=82, nb_lo=300, nb_hi=500, cg_frac=0.03)
     raw = rb.raw.astype(np.int32)
