@@ -228,22 +228,28 @@ __global__ void lut_kernel(const int64_t* __restrict__ lut_off, const int32_t* _
 
 // numpy's pairwise summation (DOUBLE_pairwise_sum): < 8 sequential, <= 128 eight-way unrolled, else halves.
 template <class F> __device__ double pairwise_block(const F& f, int a0, int n) {
-  if (n < 8) {
-    double res = 0.0;
-    for (int i = 0; i < n; ++i) res = __dadd_rn(res, f(a0 + i));
-    return res;
-  }
-  double r[8];
+  // The additions happen in numpy's order; the (dependent raw -> LUT) loads of the sequential parts are issued together
+  // first, so that their latencies overlap instead of adding up element by element.
+  double res = 0.0;
+  int i = 0;
+  if (n >= 8) {
+    double r[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = f(a0 + j);
-  int i = 8;
-  for (; i < n - (n % 8); i += 8) {
+    for (int j = 0; j < 8; ++j) r[j] = f(a0 + j);
+    for (i = 8; i < n - (n % 8); i += 8) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(a0 + i + j));
+      for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(a0 + i + j));
+    }
+    res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                    __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
   }
-  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-  for (; i < n; ++i) res = __dadd_rn(res, f(a0 + i));
+  const int nt = n - i;                                  // fewer than 8 left (the whole slice when n < 8): sequential adds
+  double t[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) t[j] = j < nt ? f(a0 + i + j) : 0.0;
+#pragma unroll
+  for (int j = 0; j < 7; ++j)
+    if (j < nt) res = __dadd_rn(res, t[j]);
   return res;
 }
 // The n > 128 recursion of numpy (split at n/2 rounded down to a multiple of 8) with an explicit stack; `leaf(a0, n)`
