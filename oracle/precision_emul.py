@@ -9,7 +9,9 @@ rounding to fp16 / bf16 at every point where the CUDA path stores a 16-bit value
   w_blk     inception weights              a_planes  P3 / P4 / P5 / stem planes
   w_lstm    LSTM kernels + embedding LUT   a_u       b5b output (U)
   a_feat    mean / std / len feature rows  a_y       block outputs (optionally only some blocks)
-  a_h       h_t of every LSTM step
+  a_h       h_t of every LSTM step         a_b1in    the pooled block input that feeds branch 1 (not in ALL_SITES: a no-op
+                                                     when a_y already rounds the block input; study site of a rejected
+                                                     variant of the split mode, profiles/r2_ablation.md)
 
 `split_*` names in the site set select hi+lo operands (error ~2^-22) for that class instead of
 a single rounding.  Used by tests/test_precision_budget.py and to decide where the kernels keep
@@ -79,7 +81,7 @@ class Emul:
         self.cur_block = i
         c = lambda inp, sub, conv, bn, relu=True: self.cb(inp, sc + sub + "/" + conv, sc + sub + "/" + bn, "w_blk", relu)
         r5 = "branch5_residual_1x3"
-        b1 = c(MO.maxpool_same(x, 3, 1), "branch1_maxpooling", "conv1a_1x1", "bn")
+        b1 = c(self.r("a_b1in", MO.maxpool_same(x, 3, 1)), "branch1_maxpooling", "conv1a_1x1", "bn")
         b2 = c(x, "branch2_1x1", "conv0b_1x1", "bn")
         p3 = self.r("a_planes", c(x, "branch3_1x3", "conv0c_1x1", "bn1"))
         p4 = self.r("a_planes", c(x, "branch4_1x5", "conv0d_1x1", "bn1"))
