@@ -13,9 +13,9 @@ DSB_ERR_CAPACITY = -5
 DSB_ERR_NONFINITE = -8
 ABI_VERSION = 2
 FLAG_CNN, FLAG_RNN, FLAG_BASE = 1, 2, 4
-PREC_FP32, PREC_BF16, PREC_FP16, PREC_FP16X2 = 0, 1, 2, 3
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, "fp16x2": PREC_FP16X2,
-              0: PREC_FP32, 1: PREC_BF16, 2: PREC_FP16, 3: PREC_FP16X2}
+PREC_FP32, PREC_BF16, PREC_FP16, PREC_FP16X2, PREC_FP16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, "fp16x2": PREC_FP16X2, "fp16x3": PREC_FP16X3,
+              0: PREC_FP32, 1: PREC_BF16, 2: PREC_FP16, 3: PREC_FP16X2, 4: PREC_FP16X3}
 # the tensor-core mode that meets BASELINE's 2e-3 / 99.9 % tolerance on spread-logit checkpoints
 DEFAULT_PRECISION = "fp16x2"
 

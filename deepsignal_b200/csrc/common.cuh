@@ -178,7 +178,7 @@ struct dsb_ctx {
   bool have_model = false;
   dsb::FoldedModel model;
   dsb::Profiler prof;
-  std::unique_ptr<dsb::ForwardPlan, dsb::PlanDeleter> plan[4];   // per precision
+  std::unique_ptr<dsb::ForwardPlan, dsb::PlanDeleter> plan[5];   // per precision
   dsb_plan_options opts{1, 1, 1, 0, 0, 0, 0, 0};
   int* nonfinite_dev = nullptr;   // device counter written by the head kernel
   std::unique_ptr<dsb::ExtractWork, dsb::ExtractDeleter> xw;

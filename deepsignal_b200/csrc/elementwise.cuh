@@ -165,51 +165,11 @@ __global__ void pool3s1_kernel(const T* __restrict__ x, T* __restrict__ y, int64
   a.store(y + r * ld + c);
 }
 
-// ---- split-operand variants: a value is the pair (hi, lo) with v = hi + lo, |lo| <= ulp(hi)/2.  hi is a monotone
-// rounding of v, so ordering pairs by hi and then by lo orders them by v exactly; the pooled pair is one of the inputs.
-struct Pair8 {
-  float h[8], l[8];
-  __device__ __forceinline__ static Pair8 load(const __half* p, long long lo_off) {
-    Pair8 r;
-    const Vec8<__half> a = Vec8<__half>::load(p), b = Vec8<__half>::load(p + lo_off);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { r.h[i] = a.v[i]; r.l[i] = b.v[i]; }
-    return r;
-  }
-  __device__ __forceinline__ void take_max(const Pair8& o) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      // a NaN part wins as well: an overflowed activation must stay visible to the head kernel's non-finite check
-      const bool gt = o.h[i] > h[i] || (o.h[i] == h[i] && o.l[i] > l[i]) || o.h[i] != o.h[i] || o.l[i] != o.l[i];
-      h[i] = gt ? o.h[i] : h[i];
-      l[i] = gt ? o.l[i] : l[i];
-    }
-  }
-  __device__ __forceinline__ void store(__half* p, long long lo_off) const {
-    Vec8<__half> a, b;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { a.v[i] = h[i]; b.v[i] = l[i]; }
-    a.store(p);
-    b.store(p + lo_off);
-  }
-};
-
-__global__ void pool3s1_split_kernel(const __half* __restrict__ x, __half* __restrict__ y, int64_t M, int C, int ld,
-                                     long long lo_in, long long lo_out) {
-  const int cv = C / 8;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * cv) return;
-  const int64_t r = idx / cv;
-  const int c = (int)(idx % cv) * 8;
-  Pair8 a = Pair8::load(x + r * ld + c, lo_in);
-  if (r > 0) a.take_max(Pair8::load(x + (r - 1) * ld + c, lo_in));
-  if (r + 1 < M) a.take_max(Pair8::load(x + (r + 1) * ld + c, lo_in));
-  a.store(y + r * ld + c, lo_out);
-}
-
 // ---- maxpool 1x3 stride 2 SAME between stages, 16-bit activations: one warp per output row, lanes over 16-byte channel
-// vectors (coalesced 480-byte row segments), packed half2 / bf162 maxima that keep NaN, 32-bit index math.  SPLIT: the
-// value is the pair (hi, lo); the winner has the largest hi and, among equal hi, the largest lo (see Pair8).
+// vectors (coalesced 480-byte row segments), packed half2 / bf162 maxima that keep NaN, 32-bit index math.  SPLIT: a
+// value is the pair (hi, lo) with v = hi + lo, |lo| <= ulp(hi)/2; hi is a monotone rounding of v, so ordering pairs by hi
+// and then by lo orders them by v exactly: the winner has the largest hi and, among equal hi, the largest lo.  With
+// stride 1 the same kernel is the branch-1 pool of the un-fused plan.
 template <bool F16> __device__ __forceinline__ uint32_t pmax_nan(uint32_t a, uint32_t b) {
   if constexpr (F16) {
     const __half2 r = __hmax2_nan(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
@@ -233,7 +193,8 @@ __device__ __forceinline__ void pair_max2(uint32_t& ah, uint32_t& al, uint32_t b
 
 template <bool SPLIT, bool F16>
 __global__ void __launch_bounds__(256) pool3s2_16_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int rows_out, int cv, int ld,
-                                                        int Lin, int Lpin, int Lout, int Lpout, int pl, long long lo_in, long long lo_out) {
+                                                        int Lin, int Lpin, int Lout, int Lpout, int pl, long long lo_in, long long lo_out,
+                                                        int stride = 2) {
   const int lane = threadIdx.x & 31;
   const int nwarps = (int)(gridDim.x * (blockDim.x >> 5));
   for (int row = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); row < rows_out; row += nwarps) {
@@ -243,7 +204,7 @@ __global__ void __launch_bounds__(256) pool3s2_16_kernel(const uint16_t* __restr
       if (po < Lout) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const int q = 2 * po - pl + k;
+          const int q = stride * po - pl + k;           // stride 2 between stages; stride 1 = the branch-1 pool of the un-fused plan
           if (q < 0 || q >= Lin) continue;
           const uint16_t* src = x + ((size_t)s * Lpin + q) * ld + c * 8;
           const uint4 vh = __ldg(reinterpret_cast<const uint4*>(src));

@@ -81,14 +81,18 @@ struct Arena {          // bump allocator over one DevBuf (two passes: size, the
   }
 };
 
-template <class T> struct DevGemm { const T* w; const float* bias; int N; int Ktot; };
+// Ktot: columns of the device matrix; Klo: column where the lo parts of the weights start (0 = single-rounded weights)
+template <class T> struct DevGemm { const T* w; const float* bias; int N; int Ktot; int Klo = 0; };
 
 // Upload a folded GEMM: K is re-laid out as the concatenation of `parts` (src_k0, len, padded_len).
 template <class T>
-DevGemm<T> upload_gemm(Arena& wa, const FoldedGemm& g, const std::vector<std::array<int, 3>>& parts, cudaStream_t s) {
-  int Ktot = 0;
-  for (auto& p : parts) Ktot += p[2];
-  DevGemm<T> d{nullptr, nullptr, g.N, Ktot};
+DevGemm<T> upload_gemm(Arena& wa, const FoldedGemm& g, const std::vector<std::array<int, 3>>& parts, cudaStream_t s,
+                       bool with_lo = false) {
+  int K1 = 0;
+  for (auto& p : parts) K1 += p[2];
+  // with_lo (DSB_PREC_FP16X3): [N][K1 | K1] = fp16(w) followed by fp16(w - fp16(w)), the third term of the split product
+  const int Ktot = with_lo ? 2 * K1 : K1;
+  DevGemm<T> d{nullptr, nullptr, g.N, Ktot, with_lo ? K1 : 0};
   T* w = reinterpret_cast<T*>(wa.take((size_t)g.N * Ktot * sizeof(T)));
   float* b = reinterpret_cast<float*>(wa.take((size_t)g.N * sizeof(float)));
   d.w = w;
@@ -101,8 +105,11 @@ DevGemm<T> upload_gemm(Arena& wa, const FoldedGemm& g, const std::vector<std::ar
         for (int k = 0; k < p[2]; ++k) {
           const float v = (k < p[1]) ? g.w[(size_t)n * g.K + p[0] + k] : 0.f;
           if constexpr (std::is_same<T, float>::value) h[(size_t)n * Ktot + ko + k] = v;
-          else if constexpr (std::is_same<T, __half>::value) h[(size_t)n * Ktot + ko + k] = __float2half_rn(v);
-          else h[(size_t)n * Ktot + ko + k] = __float2bfloat16_rn(v);
+          else if constexpr (std::is_same<T, __half>::value) {
+            const __half hi = __float2half_rn(v);
+            h[(size_t)n * Ktot + ko + k] = hi;
+            if (with_lo) h[(size_t)n * Ktot + K1 + ko + k] = __float2half_rn(v - __half2float(hi));
+          } else h[(size_t)n * Ktot + ko + k] = __float2bfloat16_rn(v);
         }
         ko += p[2];
       }
@@ -127,6 +134,7 @@ struct Builder {
   Arena wa, ba;       // weights, work buffers
   bool place;         // second pass: pointers are real
   cudaStream_t up_stream;
+  bool w3 = false;    // DSB_PREC_FP16X3: weights as hi + lo too (three product terms), one launch per conv
 
   T* buf(size_t elems) { return reinterpret_cast<T*>(ba.take(elems * sizeof(T))); }
   // CNN activation matrix; in split mode its lo twin follows it (`elems` elements further on)
@@ -176,15 +184,17 @@ struct Builder {
       for (size_t i = 0; i < segs.size(); ++i) {
         const int nkb = round_up(segs[i].K, BK) / BK;
         const int wkb = kt / BK;
-        if (ns + (segs[i].lo ? 2 : 1) > MAX_SEG) fail(DSB_ERR_STATE, "internal: too many GEMM segments");
+        if (ns + (segs[i].lo ? 2 : 1) + (W.Klo ? 1 : 0) > MAX_SEG) fail(DSB_ERR_STATE, "internal: too many GEMM segments");
         L.p.seg[ns++] = SegTC{map_of(segs[i].a, segs[i]), segs[i].col0, segs[i].drow, nkb, wkb};
         if (segs[i].lo)      // the lo part multiplies the same weight blocks
           L.p.seg[ns++] = SegTC{map_of(reinterpret_cast<const T*>(segs[i].a) + segs[i].lo, segs[i]), segs[i].col0, segs[i].drow, nkb, wkb};
+        if (W.Klo)           // third term: hi activations x lo weights (xl . wl ~ 2^-22 is dropped)
+          L.p.seg[ns++] = SegTC{map_of(segs[i].a, segs[i]), segs[i].col0, segs[i].drow, nkb, wkb + W.Klo / BK};
         kt += nkb * BK;
       }
       L.p.nseg = ns;
       if (nmaps == 1) L.maps.a[1] = L.maps.a[0];
-      if (kt != W.Ktot) fail(DSB_ERR_STATE, "internal: 16-bit GEMM K mismatch %d vs %d", kt, W.Ktot);
+      if (kt != (W.Klo ? W.Klo : W.Ktot)) fail(DSB_ERR_STATE, "internal: 16-bit GEMM K mismatch %d vs %d", kt, W.Klo ? W.Klo : W.Ktot);
       L.p.BN = W.N <= 256 ? W.N : 256;
       L.p.epi = epi;
       L.flops_per_row = st.flops_per_row;
@@ -226,8 +236,8 @@ struct Builder {
         DSB_CUDA(cudaMemcpyAsync(w1, fm.conv1.w.data(), 64 * 7 * sizeof(float), cudaMemcpyHostToDevice, up_stream));
         DSB_CUDA(cudaMemcpyAsync(b1, fm.conv1.bias.data(), 64 * sizeof(float), cudaMemcpyHostToDevice, up_stream));
       }
-      DevGemm<T> Wc2 = upload_gemm<T>(wa, fm.conv2, kparts({{0, 64}}, 64), up_stream);
-      DevGemm<T> Wc3 = upload_gemm<T>(wa, fm.conv3, tap_parts(3, 128, 64), up_stream);
+      DevGemm<T> Wc2 = upload_gemm<T>(wa, fm.conv2, kparts({{0, 64}}, 64), up_stream, w3);
+      DevGemm<T> Wc3 = upload_gemm<T>(wa, fm.conv3, tap_parts(3, 128, 64), up_stream, w3);
       // ---- buffers (split mode: every matrix is followed by its lo twin) ----
       constexpr int YLD = 256;            // 240 channels padded to a 512-byte row pitch: every TMA row chunk is one aligned 128-byte line
       const size_t eP1 = (size_t)R2 * 64, eC2 = (size_t)R2 * 128, eX = (size_t)R2 * 256, eY = (size_t)R2 * YLD;
@@ -255,7 +265,7 @@ struct Builder {
       const int conv_total = std::max((fm.L1 - 1) * 2 + 7 - S, 0);
       const int pool_total = std::max((L2 - 1) * 2 + 3 - fm.L1, 0);
       // un-fused reference (fused_front = 0): stem on the CUDA cores in fp32 followed by conv2 / conv3 as generic GEMM launches
-      const bool front = TC && opt.fused_front != 0;
+      const bool front = TC && opt.fused_front != 0 && !w3;
       T* wB1 = reinterpret_cast<T*>(wa.take((size_t)192 * 64 * sizeof(T)));
       if (front) {
         if constexpr (TC) {
@@ -322,13 +332,13 @@ struct Builder {
         const FoldedBlock& fb = fm.blocks[i];
         const int cin = fb.cin;
         const int64_t rows_cap = cap * Lp;
-        DevGemm<T> Wb1 = upload_gemm<T>(wa, fb.b1, kparts({{0, cin}}, 64), up_stream);
-        DevGemm<T> Wp1 = upload_gemm<T>(wa, fb.p1, kparts({{0, cin}}, 64), up_stream);
-        DevGemm<T> Wb3 = upload_gemm<T>(wa, fb.b3, tap_parts(3, 32, 32), up_stream);
-        DevGemm<T> Wb4 = upload_gemm<T>(wa, fb.b4, tap_parts(5, 32, 32), up_stream);
-        DevGemm<T> Wb5b = upload_gemm<T>(wa, fb.b5b, tap_parts(3, 32, 32), up_stream);
-        DevGemm<T> Wb5c = upload_gemm<T>(wa, fb.b5c, kparts({{0, 64}}, 64), up_stream);
-        const bool fused = TC && opt.fused_blocks != 0;
+        DevGemm<T> Wb1 = upload_gemm<T>(wa, fb.b1, kparts({{0, cin}}, 64), up_stream, w3);
+        DevGemm<T> Wp1 = upload_gemm<T>(wa, fb.p1, kparts({{0, cin}}, 64), up_stream, w3);
+        DevGemm<T> Wb3 = upload_gemm<T>(wa, fb.b3, tap_parts(3, 32, 32), up_stream, w3);
+        DevGemm<T> Wb4 = upload_gemm<T>(wa, fb.b4, tap_parts(5, 32, 32), up_stream, w3);
+        DevGemm<T> Wb5b = upload_gemm<T>(wa, fb.b5b, tap_parts(3, 32, 32), up_stream, w3);
+        DevGemm<T> Wb5c = upload_gemm<T>(wa, fb.b5c, kparts({{0, 64}}, 64), up_stream, w3);
+        const bool fused = TC && opt.fused_blocks != 0 && !w3;
         if (fused) {
           if constexpr (TC) {
             const bool f16 = std::is_same<T, __half>::value;
@@ -402,6 +412,7 @@ struct Builder {
             st.stream = 0;
             st.rows_per_sample = Lp;
             st.src = X; st.dst = XP; st.C = cin; st.ld = xld; st.lo_in = xlo; st.lo_out = loX;
+            st.Lin = L; st.Lpin = Lp; st.Lout = L; st.Lpout = Lp; st.pl = 1;
             plan.steps.push_back(st);
           }
           gemm(0, Lp, rows_cap, {SegHost{XP, xld, cin, 0, 0, cin, Lp, loX}}, Wb1, 64, conv_epi(Y, YLD, 0, 0xffffffffu, Lp, L, loY), EPI_CONV, KC_GEMM, L, cin);
@@ -557,11 +568,12 @@ struct Builder {
 };
 
 template <class T, bool SPLIT>
-void build_plan(dsb_ctx* ctx, ForwardPlan& plan, int64_t cap, cudaStream_t s) {
+void build_plan(dsb_ctx* ctx, ForwardPlan& plan, int64_t cap, cudaStream_t s, bool w3 = false) {
   // pass 1: sizes
   {
     ForwardPlan scratch;
     Builder<T, SPLIT> b{ctx, scratch, ctx->model, cap, Arena{}, Arena{}, false, s};
+    b.w3 = w3;
     b.build();
     plan.weights.ensure(b.wa.off + 1024);
     plan.work.ensure(b.ba.off + 1024);
@@ -573,6 +585,7 @@ void build_plan(dsb_ctx* ctx, ForwardPlan& plan, int64_t cap, cudaStream_t s) {
   wa.base = reinterpret_cast<uint8_t*>(plan.weights.p);
   ba.base = reinterpret_cast<uint8_t*>(plan.work.p);
   Builder<T, SPLIT> b{ctx, plan, ctx->model, cap, wa, ba, true, s};
+  b.w3 = w3;
   b.build();
   DSB_CUDA(cudaStreamSynchronize(s));
   plan.cap = cap;
@@ -664,9 +677,13 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
       case ST_POOL1: {
         Timer tm(ctx, s, KC_ELEM, 0);
         const int64_t total = M * (st.C / 8);
-        if constexpr (SPLIT)
-          pool3s1_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __half*>(st.src), reinterpret_cast<__half*>(st.dst), M, st.C, st.ld, st.lo_in, st.lo_out);
-        else
+        if constexpr (SPLIT) {
+          // the warp-per-row pool kernel of the stage boundaries with stride 1 (6 TB/s against 3.6 for the per-vector kernel)
+          const int rows_out = (int)M;
+          const unsigned grid = (unsigned)std::min<int64_t>((rows_out + 7) / 8, (int64_t)ctx->sm_count * 16);
+          pool3s2_16_kernel<true, true><<<grid, 256, 0, s>>>(reinterpret_cast<const uint16_t*>(st.src), reinterpret_cast<uint16_t*>(st.dst), rows_out,
+                                                             st.C / 8, st.ld, st.Lin, st.Lpin, st.Lout, st.Lpout, st.pl, st.lo_in, st.lo_out, 1);
+        } else
           pool3s1_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const T*>(st.src), reinterpret_cast<T*>(st.dst), M, st.C, st.ld);
         DSB_CUDA(cudaGetLastError());
         ctx->launches++;
@@ -733,9 +750,10 @@ void run_chunk(dsb_ctx* ctx, ForwardPlan& plan, int64_t n, const int32_t* kmer, 
 }  // namespace
 
 template <class T, bool SPLIT>
-size_t plan_bytes(const dsb_ctx* ctx, int64_t chunk) {
+size_t plan_bytes(const dsb_ctx* ctx, int64_t chunk, bool w3 = false) {
   ForwardPlan scratch;
   Builder<T, SPLIT> b{const_cast<dsb_ctx*>(ctx), scratch, ctx->model, chunk, Arena{}, Arena{}, false, nullptr};
+  b.w3 = w3;
   b.build();
   return b.ba.off + b.wa.off;
 }
@@ -747,6 +765,7 @@ size_t forward_workspace_bytes(const dsb_ctx* ctx, int64_t chunk, int precision)
     case DSB_PREC_FP32: bytes = plan_bytes<float, false>(ctx, chunk); break;
     case DSB_PREC_FP16: bytes = plan_bytes<__half, false>(ctx, chunk); break;
     case DSB_PREC_FP16X2: bytes = plan_bytes<__half, true>(ctx, chunk); break;
+    case DSB_PREC_FP16X3: bytes = plan_bytes<__half, true>(ctx, chunk, true); break;
     case DSB_PREC_BF16: bytes = plan_bytes<__nv_bfloat16, false>(ctx, chunk); break;
     default: return 0;
   }
@@ -756,7 +775,7 @@ size_t forward_workspace_bytes(const dsb_ctx* ctx, int64_t chunk, int precision)
 void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, const float* means, const float* stds,
                  const float* lens, const float* signals, float* probs, int32_t* pred, cudaStream_t stream) {
   if (!ctx->have_model) fail(DSB_ERR_STATE, "dsb_forward called before dsb_load_weights");
-  if (precision < DSB_PREC_FP32 || precision > DSB_PREC_FP16X2) fail(DSB_ERR_INVALID, "unknown precision %d", precision);
+  if (precision < DSB_PREC_FP32 || precision > DSB_PREC_FP16X3) fail(DSB_ERR_INVALID, "unknown precision %d", precision);
   if (n < 0) fail(DSB_ERR_INVALID, "negative sample count");
   if (n == 0) return;
   if (!signals || !probs || !pred || (ctx->model.has_rnn() && (!means || !stds || !lens || (ctx->model.has_base() && !kmer))))
@@ -783,6 +802,7 @@ void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, co
       case DSB_PREC_FP32: build_plan<float, false>(ctx, *np, want, stream); break;
       case DSB_PREC_FP16: build_plan<__half, false>(ctx, *np, want, stream); break;
       case DSB_PREC_FP16X2: build_plan<__half, true>(ctx, *np, want, stream); break;
+      case DSB_PREC_FP16X3: build_plan<__half, true>(ctx, *np, want, stream, true); break;
       default: build_plan<__nv_bfloat16, false>(ctx, *np, want, stream); break;
     }
     slot = std::move(np);
@@ -801,7 +821,7 @@ void forward_dev(dsb_ctx* ctx, int precision, int64_t n, const int32_t* kmer, co
     switch (precision) {
       case DSB_PREC_FP32: run_chunk<float, false>(ctx, plan, m, k, mu, sd, ln, sg, pr, pd, stream); break;
       case DSB_PREC_FP16: run_chunk<__half, false>(ctx, plan, m, k, mu, sd, ln, sg, pr, pd, stream); break;
-      case DSB_PREC_FP16X2: run_chunk<__half, true>(ctx, plan, m, k, mu, sd, ln, sg, pr, pd, stream); break;
+      case DSB_PREC_FP16X2: case DSB_PREC_FP16X3: run_chunk<__half, true>(ctx, plan, m, k, mu, sd, ln, sg, pr, pd, stream); break;
       default: run_chunk<__nv_bfloat16, false>(ctx, plan, m, k, mu, sd, ln, sg, pr, pd, stream); break;
     }
   }

@@ -11,7 +11,7 @@
 
 namespace dsb {
 
-constexpr int MAX_SEG = 10;         // 5 taps x (hi, lo) parts in the split-operand mode
+constexpr int MAX_SEG = 15;         // 5 taps x (hi.wh, lo.wh, hi.wl) product terms in the three-term split mode
 
 enum EpiKind { EPI_CONV = 0, EPI_LSTM = 1 };
 

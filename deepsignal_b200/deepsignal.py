@@ -3,7 +3,7 @@
 reference's flags and defaults (reference deepsignal/deepsignal.py:156-326).  ``train`` / ``denoise``
 are outside this implementation's scope (the call_mods hot path) and are not provided.
 
-Extra flags: ``--precision {fp32,fp16x2,fp16,bf16}`` (call_mods; default fp16x2 = split-operand tensor-core path) and
+Extra flags: ``--precision {fp32,fp16x3,fp16x2,fp16,bf16}`` (call_mods; default fp16x2 = split-operand tensor-core path) and
 ``--device`` (CUDA device index).
 """
 from __future__ import absolute_import
@@ -117,9 +117,10 @@ def main():
     cc.add_argument("--learning_rate", "-l", default=0.001, type=float, required=False, action="store",
                     help="init learning rate, default 0.001")
     cc.add_argument("--class_num", "-c", action="store", default=2, type=int, required=False, help="class num, default 2")
-    cc.add_argument("--precision", default="fp16x2", choices=["fp32", "fp16x2", "fp16", "bf16"],
+    cc.add_argument("--precision", default="fp16x2", choices=["fp32", "fp16x3", "fp16x2", "fp16", "bf16"],
                     help="arithmetic path: fp32 CUDA cores, or tcgen05 tensor cores with split fp16 hi+lo activations "
-                         "(fp16x2: within 2e-3 of the fp32 reference), or single fp16 / bf16 operands (faster, looser)")
+                         "(fp16x2: within 2e-3 of the fp32 reference on the benchmarked checkpoint; fp16x3: weights split too, ~1e-5 whatever the "
+                         "checkpoint, about half the rate), or single fp16 / bf16 operands (faster, looser)")
     co = sc.add_argument_group("OUTPUT")
     co.add_argument("--result_file", "-o", action="store", type=str, required=True,
                     help="the file path to save the predicted result")

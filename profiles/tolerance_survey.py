@@ -28,7 +28,7 @@ def main():
             eng.load_weights(ck, **kw)
             ref, _ = mo.forward(ck, *x, **kw)
             out = {"seed": seed, "variant": kw, "n": n}
-            for prec in ("fp16x2", "fp16"):
+            for prec in ("fp16x3", "fp16x2", "fp16"):
                 got, pred = eng.forward(*x, precision=prec)
                 out[prec] = float(np.abs(got - ref).max())
             print(json.dumps(out), flush=True)

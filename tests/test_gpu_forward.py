@@ -22,6 +22,7 @@ pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-4
 TC_TOL = 2e-3          # BASELINE tolerance of the 16-bit tensor-core path: asserted for the default mode fp16x2
+X3_TOL = 1e-4          # three-term split mode (weights hi + lo too): the fp32 path's tolerance, whatever the checkpoint
 MIN_IDENTICAL = 0.999
 FAST_MODE_BOUNDS = {"fp16": 4e-3, "bf16": 6e-2}     # characterisation of the non-default single-rounding modes
 
@@ -126,7 +127,7 @@ def test_default_mode_tolerance_at_100k_samples(engine, ckpt):
 
 
 @pytest.mark.parametrize("kw", [dict(is_cnn=False), dict(is_rnn=False), dict(is_base=False)])
-@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("fp16x2", TC_TOL), ("fp16", FAST_MODE_BOUNDS["fp16"]),
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("fp16x3", X3_TOL), ("fp16x2", TC_TOL), ("fp16", FAST_MODE_BOUNDS["fp16"]),
                                            ("bf16", FAST_MODE_BOUNDS["bf16"])])
 def test_model_variants(engine, kw, precision, tol):
     ck = W.random_checkpoint(23, "stress", **kw)
@@ -321,3 +322,20 @@ def test_repeated_runs_are_bit_identical(engine, ckpt, precision):
     for _ in range(6):
         got, pred = engine.forward(*x, precision=precision)
         assert np.array_equal(got, ref) and np.array_equal(pred, pref)
+
+
+def test_three_term_split_mode_is_checkpoint_independent(engine):
+    """fp16x3 (activations AND weights as hi + lo fp16, three product terms on tcgen05): within the fp32 path's 1e-4 on
+    checkpoints where the default fp16x2 mode -- whose residual is the fp16 rounding of the CNN weights -- leaves 2e-3
+    (profiles/r2_tolerance_survey.jsonl), and identical calls."""
+    x = _inputs(1024, 104)
+    for seed in (17, 47, 59):
+        ck = W.random_checkpoint(seed, "stress")
+        engine.load_weights(ck)
+        ref, ref_pred = mo.forward(ck, *x)
+        got, pred = engine.forward(*x, precision="fp16x3")
+        err = np.abs(got - ref).max()
+        print("seed", seed, "fp16x3 max|dp|", err)
+        assert err <= X3_TOL
+        margin = np.abs(ref[:, 0] - ref[:, 1])
+        assert not np.any((pred != ref_pred) & (margin > X3_TOL))
