@@ -26,9 +26,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-CASES = [  # (name, checkpoint seed, variant, feature seed, n)
-    ("stress17", 17, "stress", 101, 6),
-    ("tfdefault23", 23, "tf_default", 102, 4),
+CASES = [  # (name, checkpoint seed, variant, feature seed, n, Model(...) switches)
+    ("stress17", 17, "stress", 101, 6, {}),
+    ("tfdefault23", 23, "tf_default", 102, 4, {}),
+    ("stress31_no_base", 31, "stress", 103, 3, {"is_base": False}),      # model.py:57-76: features only, no embedding
+    ("stress31_no_rnn", 31, "stress", 103, 3, {"is_rnn": False}),        # model.py:88-94: signal model alone
+    ("stress31_no_cnn", 31, "stress", 103, 3, {"is_cnn": False}),        # event model alone (the signal model is still built)
 ]
 
 
@@ -39,7 +42,7 @@ def reference_dir():
     return None
 
 
-def run_reference_model(ckpt, kmer, means, stds, lens, signals, ref_pkg_dir):
+def run_reference_model(ckpt, kmer, means, stds, lens, signals, ref_pkg_dir, **model_kw):
     """-> (activation_logits [n,2] f64, prediction [n], names of the variables the graph code asked for, in order)."""
     from oracle import tf_shim
     saved = tf_shim.install()
@@ -54,7 +57,7 @@ def run_reference_model(ckpt, kmer, means, stds, lens, signals, ref_pkg_dir):
         n = len(kmer)
         # placeholders in creation order (model.py:31-42): base_int, means, stds, sanums, signals, labels, lr, keep_prob, training
         tf_shim.begin(ckpt, [kmer, means, stds, lens, signals, np.zeros(n, np.int32), 0.001, 1.0, False])
-        m = ref_model.Model(base_num=kmer.shape[1], signal_num=signals.shape[1], class_num=2)
+        m = ref_model.Model(base_num=kmer.shape[1], signal_num=signals.shape[1], class_num=2, **model_kw)
         return np.asarray(m.activation_logits, np.float64), np.asarray(m.prediction), tf_shim.variables_used()
     finally:
         for k in [k for k in sys.modules if k == pkg_name or k.startswith(pkg_name + ".")]:
@@ -74,12 +77,12 @@ def main():
     if ref is None:
         raise SystemExit("reference sources not found (set DEEPSIGNAL_REFERENCE)")
     out = {"generator": "tests/golden/make_model_golden.py", "cases": {}}
-    for name, ck_seed, variant, f_seed, n in CASES:
-        ck = W.random_checkpoint(ck_seed, variant)
+    for name, ck_seed, variant, f_seed, n, kw in CASES:
+        ck = W.random_checkpoint(ck_seed, variant, **kw)
         kmer, means, stds, lens, signals = case_inputs(f_seed, n)
-        act, pred, used = run_reference_model(ck, kmer, means, stds, lens, signals, ref)
+        act, pred, used = run_reference_model(ck, kmer, means, stds, lens, signals, ref, **kw)
         out["cases"][name] = {
-            "checkpoint": [ck_seed, variant], "features_seed": f_seed, "n": n,
+            "checkpoint": [ck_seed, variant], "model_kw": kw, "features_seed": f_seed, "n": n,
             "activation_logits": [[repr(float(v)) for v in row] for row in act],
             "prediction": [int(v) for v in pred],
             "n_variables": len(used),

@@ -429,3 +429,17 @@ def test_block_from_info_formats_like_call_mods():
     bad[3, 4] = 255
     with pytest.raises(KeyError):
         block_from_info(info, bad)
+
+
+def test_synth_force_lens_does_not_disturb_the_random_stream():
+    """`force_lens` only overwrites dwell times: every read generated without it must stay byte-identical (the golden
+    fixtures and the bench workloads are seeded)."""
+    from deepsignal_b200.synth import synth_reads
+    a = synth_reads(3, seed=5, nb_lo=100, nb_hi=150)
+    b = synth_reads(3, seed=5, nb_lo=100, nb_hi=150, force_lens={})
+    c = synth_reads(3, seed=5, nb_lo=100, nb_hi=150, force_lens={7: 300})
+    assert np.array_equal(a.raw, b.raw) and np.array_equal(a.ev_len, b.ev_len)
+    assert np.array_equal(a.ev_base, c.ev_base) and c.ev_len[7] == 300
+    keep = np.ones(len(a.ev_len), bool)
+    keep[7] = False
+    assert np.array_equal(a.ev_len[keep], c.ev_len[keep])

@@ -31,19 +31,20 @@ def _cases():
     return json.load(open(GOLDEN))["cases"]
 
 
-@pytest.mark.parametrize("name", ["stress17", "tfdefault23"])
+@pytest.mark.parametrize("name", ["stress17", "tfdefault23", "stress31_no_base", "stress31_no_rnn", "stress31_no_cnn"])
 def test_oracle_matches_reference_graph_code(name):
     c = _cases()[name]
-    ck = W.random_checkpoint(*c["checkpoint"])
+    kw = c.get("model_kw", {})
+    ck = W.random_checkpoint(*c["checkpoint"], **kw)
     kmer, means, stds, lens, signals = _gen().case_inputs(c["features_seed"], c["n"])
     want = np.asarray([[float(v) for v in row] for row in c["activation_logits"]], np.float64)
-    got, pred = mo.forward(ck, kmer, means, stds, lens, signals)
+    got, pred = mo.forward(ck, kmer, means, stds, lens, signals, **kw)
     # both sides are float64; they differ only in summation order (einsum / matmul vs conv1d)
     assert np.max(np.abs(got - want)) <= 1e-10
     assert pred.tolist() == c["prediction"]
     # the variable names the reference's scopes generate are exactly the checkpoint's (weights.variable_specs)
-    names = [n for n, _ in W.variable_specs()]
-    assert c["n_variables"] == len(names) == len(ck)
+    names = [n for n, _ in W.variable_specs(**kw)]
+    assert c["n_variables"] == len(names) == len(ck)      # incl. the signal model's variables when is_cnn=False (model.py:83-85)
     assert set(names) == set(ck)
 
 
