@@ -30,8 +30,8 @@ pinned to the reference's own source: tests/golden/make_model_golden.py executes
 deepsignal/model.py + layers.py UNMODIFIED over a NumPy stand-in for the ~35 TF 1.x
 calls they make (oracle/tf_shim.py, written independently of this file), and
 tests/test_model_golden.py requires this oracle to reproduce those outputs to 1e-10
-on two checkpoints, with exactly the 580 variable names the reference's scopes
-generate.  The TF op semantics themselves (the bullets above) remain restated and
+on five cases (two full-model checkpoints and the is_base / is_rnn / is_cnn = False
+variants), with exactly the variable names the reference's scopes generate.  The TF op semantics themselves (the bullets above) remain restated and
 hand-checked only: **parity unpinned against real TF kernels**.
 """
 from __future__ import annotations
