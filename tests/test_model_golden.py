@@ -89,3 +89,27 @@ def test_shim_primitives_known_answers():
                    "bn/moving_variance": np.asarray([0.999])}, [])
     y = tf_shim.batch_norm(inputs=np.asarray([[5.0]]), is_training=False, scope="bn", center=True, scale=True)
     assert abs(float(y[0, 0]) - 5.0) < 1e-12
+
+
+def test_same_padding_rule_against_an_independent_tf_port():
+    """TensorFlow's asymmetric "SAME" padding (the extra sample goes to the right) restated in oracle/tf_shim.py and
+    oracle/model_oracle.py, against HuggingFace transformers' `apply_tf_padding` -- written by a third party to load
+    TF-slim checkpoints into torch and validated against them -- for every (length, kernel, stride) the model uses.
+    The same port's default batch-norm epsilon (TF-slim = tf.contrib.layers.batch_norm) is the 1e-3 used here."""
+    torch = pytest.importorskip("torch")
+    mnet = pytest.importorskip("transformers.models.mobilenet_v1.modeling_mobilenet_v1")
+    from transformers import MobileNetV1Config
+    shapes = [(360, 7, 2), (180, 3, 2), (90, 1, 1), (90, 3, 1), (90, 5, 1), (90, 3, 2), (45, 3, 1), (45, 5, 1), (45, 3, 2),
+              (23, 3, 1), (23, 5, 1), (23, 7, 1), (5, 3, 2), (6, 3, 2)]
+    for n, k, s in shapes:
+        conv = torch.nn.Conv2d(1, 1, (1, k), stride=(1, s))
+        x = torch.zeros(1, 1, 1, n)
+        x[..., 0] = 1.0
+        y = mnet.apply_tf_padding(x, conv)
+        left = int(torch.nonzero(y[0, 0, 0])[0])
+        right = y.shape[-1] - n - left
+        out, pl, pr = tf_shim._same_pad(n, k, s)
+        assert (pl, pr) == (left, right), (n, k, s)
+        assert mo.same_pads(n, k, s) == (left, right), (n, k, s)
+        assert out == -(-n // s)
+    assert MobileNetV1Config().layer_norm_eps == W.BN_EPS == 0.001
