@@ -443,3 +443,20 @@ def test_synth_force_lens_does_not_disturb_the_random_stream():
     keep = np.ones(len(a.ev_len), bool)
     keep[7] = False
     assert np.array_equal(a.ev_len[keep], c.ev_len[keep])
+
+
+def test_snappy_codec_against_a_real_snappy_implementation():
+    """deepsignal_b200/tf_bundle.py carries a pure-Python Snappy (TF's table builder compresses index blocks with it);
+    pyarrow links the real library: each side must read what the other writes."""
+    pa = pytest.importorskip("pyarrow")
+    if not pa.Codec.is_available("snappy"):
+        pytest.skip("pyarrow built without snappy")
+    from deepsignal_b200 import tf_bundle
+    codec = pa.Codec("snappy")
+    rng = np.random.default_rng(3)
+    names = b"".join(b"modelsignalmincp_layer%d/modelsignalm%dbranch3_1x3/bn1/moving_variance\x00" % (i, i) for i in range(1, 12))
+    cases = [b"a", b"abc" * 1000, bytes(rng.integers(0, 256, 70000, dtype=np.uint8)), names * 7,
+             bytes(rng.integers(0, 4, 200000, dtype=np.uint8))]
+    for d in cases:
+        assert tf_bundle.snappy_decompress(codec.compress(d, asbytes=True)) == d
+        assert codec.decompress(tf_bundle.snappy_compress(d), decompressed_size=len(d), asbytes=True) == d
